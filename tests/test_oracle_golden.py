@@ -98,8 +98,11 @@ def test_apex_target_matches_reference(golden, case):
 
 def test_value_rescaling_matches_reference(golden):
     g = golden("r2d2")
-    np.testing.assert_array_equal(O.value_transform(g["h_x"]), g["h_y"])
-    np.testing.assert_array_equal(O.value_inv_transform(g["h_x"]), g["hinv_y"])
+    # torch-CPU sqrt (Sleef, third-party) is not always correctly rounded (0.55 % of
+    # inputs are 1 ulp off IEEE sqrtf); h^-1 amplifies that by the (s-1) cancellation.
+    # The oracle and the kernels use IEEE sqrt, so the match is to the 1e-5 contract.
+    np.testing.assert_allclose(O.value_transform(g["h_x"]), g["h_y"], rtol=5e-7, atol=1e-7)
+    np.testing.assert_allclose(O.value_inv_transform(g["h_x"]), g["hinv_y"], rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("case", ["s0", "s1"])
