@@ -1,0 +1,108 @@
+// Handle management, error reporting and bookkeeping for libb2rl's C ABI
+// (include/b2rl.h).
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+
+namespace b2rl {
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" const char* b2rl_last_error(void) { return g_err; }
+extern "C" int b2rl_version(void) { return 100; }
+extern "C" int64_t b2rl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static void free_all(b2rl_replay* h) {
+  for (int f = 0; f < B2RL_MAX_FIELDS; ++f)
+    if (h->field[f]) cudaFree(h->field[f]);
+  if (h->sum) cudaFree(h->sum);
+  if (h->minv) cudaFree(h->minv);
+  if (h->tag) cudaFree(h->tag);
+  if (h->mark) cudaFree(h->mark);
+  if (h->scratch_val) cudaFree(h->scratch_val);
+}
+
+extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) {
+  B2RL_REQUIRE(d != nullptr && out != nullptr, "null argument");
+  B2RL_REQUIRE(d->capacity >= 1 && d->capacity <= (1LL << 31), "capacity must be in [1, 2^31]");
+  B2RL_REQUIRE(d->n_fields >= 0 && d->n_fields <= B2RL_MAX_FIELDS, "n_fields out of range");
+  for (int f = 0; f < d->n_fields; ++f) B2RL_REQUIRE(d->field_bytes[f] >= 1, "field_bytes must be >= 1");
+  int ndev = 0;
+  B2RL_CUDA(cudaGetDeviceCount(&ndev));
+  B2RL_REQUIRE(d->device >= 0 && d->device < ndev, "no such CUDA device");
+  DeviceGuard g(d->device);
+  b2rl_replay* h = new (std::nothrow) b2rl_replay();
+  if (!h) { set_error("out of host memory"); return B2RL_ERR_NOMEM; }
+  h->device = d->device;
+  h->capacity = d->capacity;
+  h->levels = 0;
+  h->cap2 = 1;
+  while (h->cap2 < d->capacity) { h->cap2 <<= 1; h->levels++; }
+  h->n_fields = d->n_fields;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  for (int f = 0; f < d->n_fields; ++f) {
+    h->field_bytes[f] = d->field_bytes[f];
+    // +16 B so a 16-byte bulk/vector access on the last row never leaves the allocation
+    alloc((void**)&h->field[f], (size_t)d->capacity * (size_t)d->field_bytes[f] + 16);
+  }
+  alloc((void**)&h->sum, sizeof(double) * 2 * (size_t)h->cap2);
+  alloc((void**)&h->minv, sizeof(float) * 2 * (size_t)h->cap2);
+  alloc((void**)&h->tag, sizeof(uint32_t) * (size_t)h->cap2);
+  alloc((void**)&h->mark, sizeof(int32_t) * (size_t)h->cap2);
+  alloc((void**)&h->scratch_val, sizeof(float) * (size_t)h->capacity);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc failed while creating a %lld-slot replay: %s", (long long)d->capacity,
+              cudaGetErrorString(e));
+    free_all(h);
+    delete h;
+    cudaGetLastError();
+    return B2RL_ERR_NOMEM;
+  }
+  // empty tree: sums 0, mins +inf, tags/marks 0
+  B2RL_CUDA(cudaMemset(h->sum, 0, sizeof(double) * 2 * (size_t)h->cap2));
+  B2RL_CUDA(cudaMemset(h->minv, 0x7f, sizeof(float) * 2 * (size_t)h->cap2));  // 0x7f7f7f7f ~ 3.4e38
+  B2RL_CUDA(cudaMemset(h->tag, 0, sizeof(uint32_t) * (size_t)h->cap2));
+  B2RL_CUDA(cudaMemset(h->mark, 0, sizeof(int32_t) * (size_t)h->cap2));
+  B2RL_CUDA(cudaDeviceSynchronize());
+  *out = h;
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_destroy(b2rl_replay* h) {
+  if (!h) return B2RL_OK;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  free_all(h);
+  delete h;
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_size(const b2rl_replay* h, int64_t* size, int64_t* capacity, int64_t* head) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  if (size) *size = h->size;
+  if (capacity) *capacity = h->capacity;
+  if (head) *head = h->head;
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_field_ptr(const b2rl_replay* h, int32_t field, void** ptr_dev) {
+  B2RL_REQUIRE(h != nullptr && ptr_dev != nullptr, "null argument");
+  B2RL_REQUIRE(field >= 0 && field < h->n_fields, "no such field");
+  *ptr_dev = h->field[field];
+  return B2RL_OK;
+}

@@ -1,0 +1,348 @@
+// Payload path: minibatch gather (HBM -> SMEM -> HBM through the TMA engine's
+// 1-D bulk copies), ingest (push), eviction and the synthetic counter-hash fill.
+//
+// Replaces Replay.buffer's deepcopy + pickle.loads + np.stack
+// (APE_X/ReplayMemory.py:61-116, baseline/PER.py:113) — the dominant CPU cost
+// of the reference path.
+#include "common.cuh"
+
+namespace b2rl {
+
+// ----------------------------------------------------------------------------
+// mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: UBLKCP / SYNCS)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
+// Bulk gather.  Work item = (field, sample k, chunk c); a chunk is at most
+// GATHER_CHUNK bytes of one row.  One thread per CTA drives an S-stage ring:
+//   load(item) : cp.async.bulk global -> smem, completes on mbarrier[stage]
+//   store(item): cp.async.bulk smem -> global (bulk_group)
+// The SMs only issue descriptors; the data never touches the register file.
+// ----------------------------------------------------------------------------
+constexpr int GATHER_CHUNK = 28672;  // 28 KiB, >= one (4,84,84) uint8 frame stack (28 224 B)
+constexpr int GATHER_STAGES = 8;     // 8 x 28 KiB = 224 KiB of the 227 KiB SMEM
+constexpr int GATHER_MAX_ITEMS_CACHED = 512;
+
+struct GatherField {
+  const uint8_t* src;   // field base
+  uint8_t* dst;         // output base
+  int64_t row_bytes;    // multiple of 16
+  int32_t chunks;       // ceil(row_bytes / GATHER_CHUNK)
+  int32_t pad;
+};
+struct GatherParams {
+  GatherField f[B2RL_MAX_FIELDS];
+  int32_t n_fields;
+  int32_t pad;
+  int64_t n;            // samples
+  int64_t capacity;
+  int64_t items_per_sample;  // sum of chunks over fields
+  int64_t total_items;
+};
+
+__device__ __forceinline__ void gather_decode(const GatherParams& P, const int64_t* __restrict__ idx,
+                                              int64_t item, const uint8_t*& src, uint8_t*& dst,
+                                              uint32_t& bytes) {
+  const int64_t k = item / P.items_per_sample;
+  int32_t r = (int32_t)(item - k * P.items_per_sample);
+  int f = 0;
+  while (r >= P.f[f].chunks) { r -= P.f[f].chunks; ++f; }
+  int64_t row = idx[k];
+  row = row < 0 ? 0 : (row >= P.capacity ? P.capacity - 1 : row);
+  const int64_t off = (int64_t)r * GATHER_CHUNK;
+  const int64_t rem = P.f[f].row_bytes - off;
+  bytes = (uint32_t)(rem < GATHER_CHUNK ? rem : GATHER_CHUNK);
+  src = P.f[f].src + row * P.f[f].row_bytes + off;
+  dst = P.f[f].dst + k * P.f[f].row_bytes + off;
+}
+
+__global__ void __launch_bounds__(32, 1)
+k_gather_bulk(const __grid_constant__ GatherParams P, const int64_t* __restrict__ idx) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar[GATHER_STAGES];
+  if (threadIdx.x != 0) return;  // a single thread drives the copy engine
+  for (int s = 0; s < GATHER_STAGES; ++s) mbar_init(&bar[s], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  // items of this CTA: a contiguous range, so consecutive items share idx[] cache lines
+  const int64_t per_cta = (P.total_items + gridDim.x - 1) / gridDim.x;
+  const int64_t first = (int64_t)blockIdx.x * per_cta, stride = 1;
+  const int64_t my_items =
+      (P.total_items > first) ? ((P.total_items - first < per_cta) ? P.total_items - first : per_cta) : 0;
+  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+
+  // prologue: fill the ring
+  const int64_t pre = my_items < GATHER_STAGES ? my_items : GATHER_STAGES;
+  for (int64_t t = 0; t < pre; ++t) {
+    const uint8_t* src; uint8_t* dst; uint32_t bytes;
+    gather_decode(P, idx, first + t * stride, src, dst, bytes);
+    mbar_expect_tx(&bar[t], bytes);
+    bulk_g2s(smem + (size_t)t * GATHER_CHUNK, src, bytes, &bar[t]);
+  }
+  for (int64_t t = 0; t < my_items; ++t) {
+    const int s = (int)(t % GATHER_STAGES);
+    const uint8_t* src; uint8_t* dst; uint32_t bytes;
+    gather_decode(P, idx, first + t * stride, src, dst, bytes);
+    mbar_wait(&bar[s], (phase_bits >> s) & 1u);
+    phase_bits ^= (1u << s);
+    bulk_s2g(dst, smem + (size_t)s * GATHER_CHUNK, bytes);
+    bulk_commit();
+    // refill the stage used by the PREVIOUS item once its store has drained SMEM
+    if (t >= 1) {
+      const int64_t nt = t - 1 + GATHER_STAGES;
+      if (nt < my_items) {
+        bulk_wait_read<1>();  // all but the newest store group have finished reading SMEM
+        const int ps = (int)((t - 1) % GATHER_STAGES);
+        const uint8_t* nsrc; uint8_t* ndst; uint32_t nbytes;
+        gather_decode(P, idx, first + nt * stride, nsrc, ndst, nbytes);
+        mbar_expect_tx(&bar[ps], nbytes);
+        bulk_g2s(smem + (size_t)ps * GATHER_CHUNK, nsrc, nbytes, &bar[ps]);
+      }
+    }
+  }
+  bulk_wait_all();
+}
+
+// Generic fallback / small fields: one thread per (sample, 4-byte word or byte).
+__global__ void __launch_bounds__(256)
+k_gather_small(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t row_bytes,
+               const int64_t* __restrict__ idx, int64_t n, int64_t capacity) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((row_bytes & 3) == 0) {
+    const int64_t words = row_bytes >> 2;
+    if (t >= n * words) return;
+    const int64_t k = t / words, w = t - k * words;
+    int64_t row = idx[k];
+    row = row < 0 ? 0 : (row >= capacity ? capacity - 1 : row);
+    reinterpret_cast<uint32_t*>(dst)[k * words + w] =
+        reinterpret_cast<const uint32_t*>(src)[row * words + w];
+  } else {
+    if (t >= n * row_bytes) return;
+    const int64_t k = t / row_bytes, b = t - k * row_bytes;
+    int64_t row = idx[k];
+    row = row < 0 ? 0 : (row >= capacity ? capacity - 1 : row);
+    dst[k * row_bytes + b] = src[row * row_bytes + b];
+  }
+}
+
+// LDG.128/STG.128 reference implementation of the big-row gather (kept for the
+// A/B comparison in profiles/, selectable with B2RL_GATHER=ldg).
+__global__ void __launch_bounds__(256)
+k_gather_ldg(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t row_bytes,
+             const int64_t* __restrict__ idx, int64_t n, int64_t capacity) {
+  const int64_t k = blockIdx.x;
+  if (k >= n) return;
+  int64_t row = idx[k];
+  row = row < 0 ? 0 : (row >= capacity ? capacity - 1 : row);
+  const int4* s = reinterpret_cast<const int4*>(src + row * row_bytes);
+  int4* d = reinterpret_cast<int4*>(dst + k * row_bytes);
+  const int64_t nv = row_bytes >> 4;
+  for (int64_t i = threadIdx.x; i < nv; i += 4 * 256) {
+    int4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * 256 < nv) v[u] = __ldg(s + i + u * 256);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * 256 < nv) d[i + u * 256] = v[u];
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Synthetic fill: word w of slot s of field f =
+//   lowbias32(seed ^ f*0x9E3779B9 ^ (uint32)s*2654435761 ^ (uint32)w*2246822519)
+// (tail bytes of a row whose size is not a multiple of 4 take the low bytes).
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fill_hash(uint8_t* __restrict__ base, int64_t row_bytes, int64_t n_rows, uint32_t seed, uint32_t fsalt) {
+  const int64_t words_per_row = (row_bytes + 3) >> 2;
+  const int64_t total = n_rows * words_per_row;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = t / words_per_row, w = t - s * words_per_row;
+    const uint32_t v = lowbias32(seed ^ fsalt ^ ((uint32_t)s * 2654435761U) ^ ((uint32_t)w * 2246822519U));
+    uint8_t* p = base + s * row_bytes + w * 4;
+    const int64_t left = row_bytes - w * 4;
+    if (left >= 4 && ((row_bytes & 3) == 0)) {
+      *reinterpret_cast<uint32_t*>(p) = v;
+    } else {
+      for (int b = 0; b < 4 && b < left; ++b) p[b] = (uint8_t)(v >> (8 * b));
+    }
+  }
+}
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_start,
+                          const float* vals_dev, float const_val, int64_t n, cudaStream_t st);
+
+static int gather_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("B2RL_GATHER");
+    mode = (e && e[0] == 'l') ? 1 : 0;  // "ldg" -> 1, default bulk/TMA -> 0
+  }
+  return mode;
+}
+
+extern "C" int b2rl_replay_gather(b2rl_replay* h, const int64_t* idx_dev, int64_t n,
+                                  void* const* out_fields_dev, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return B2RL_OK;
+  B2RL_REQUIRE(idx_dev != nullptr && out_fields_dev != nullptr, "null argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  GatherParams P{};
+  P.n = n;
+  P.capacity = h->capacity;
+  int nb = 0;
+  for (int f = 0; f < h->n_fields; ++f) {
+    uint8_t* out = (uint8_t*)out_fields_dev[f];
+    if (out == nullptr) continue;
+    const int64_t rb = h->field_bytes[f];
+    const bool bulk_ok = gather_mode() == 0 && (rb % 16 == 0) && rb >= 1024 &&
+                         ((uintptr_t)out % 16 == 0) && ((uintptr_t)h->field[f] % 16 == 0);
+    if (bulk_ok) {
+      P.f[nb].src = h->field[f];
+      P.f[nb].dst = out;
+      P.f[nb].row_bytes = rb;
+      P.f[nb].chunks = (int32_t)((rb + GATHER_CHUNK - 1) / GATHER_CHUNK);
+      P.items_per_sample += P.f[nb].chunks;
+      ++nb;
+    } else if (rb % 16 == 0 && rb >= 1024 && ((uintptr_t)out % 16 == 0)) {
+      k_gather_ldg<<<(unsigned)n, 256, 0, st>>>(h->field[f], out, rb, idx_dev, n, h->capacity);
+      count_launch();
+    } else {
+      const int64_t units = (rb % 4 == 0) ? n * (rb / 4) : n * rb;
+      k_gather_small<<<(unsigned)((units + 255) / 256), 256, 0, st>>>(h->field[f], out, rb, idx_dev, n,
+                                                                     h->capacity);
+      count_launch();
+    }
+  }
+  if (nb > 0) {
+    P.n_fields = nb;
+    P.total_items = P.items_per_sample * n;
+    static int sms[64] = {0};
+    static bool attr_set[64] = {false};
+    const int dev = h->device;
+    const size_t smem_bytes = (size_t)GATHER_STAGES * GATHER_CHUNK;
+    if (!attr_set[dev & 63]) {
+      B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+      B2RL_CUDA(cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+      attr_set[dev & 63] = true;
+    }
+    int64_t grid = sms[dev & 63];
+    if (grid > P.total_items) grid = P.total_items;
+    k_gather_bulk<<<(unsigned)grid, 32, smem_bytes, st>>>(P, idx_dev);
+    count_launch();
+  }
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_fill_hash(b2rl_replay* h, int64_t n, uint32_t seed, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 0 && n <= h->capacity, "n out of range");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int f = 0; f < h->n_fields; ++f) {
+    const int64_t words = n * ((h->field_bytes[f] + 3) / 4);
+    if (words == 0) continue;
+    int64_t blocks = (words + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_fill_hash<<<(unsigned)blocks, 256, 0, st>>>(h->field[f], h->field_bytes[f], n, seed,
+                                                  (uint32_t)f * 0x9E3779B9U);
+    count_launch();
+  }
+  B2RL_CHECK_LAUNCH();
+  h->size = n;
+  h->head = (n == h->capacity) ? 0 : n;
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_push(b2rl_replay* h, const void* const* fields_src, const float* prios,
+                                int64_t n, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 0 && n <= h->capacity, "n out of range (0..capacity)");
+  if (n == 0) return B2RL_OK;
+  B2RL_REQUIRE(prios != nullptr, "null priorities");
+  B2RL_REQUIRE(h->n_fields == 0 || fields_src != nullptr, "null fields");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t head = h->head;
+  const int64_t first = (head + n <= h->capacity) ? n : (h->capacity - head);  // before the wrap
+  for (int f = 0; f < h->n_fields; ++f) {
+    const uint8_t* src = (const uint8_t*)fields_src[f];
+    if (src == nullptr) continue;
+    const int64_t rb = h->field_bytes[f];
+    B2RL_CUDA(cudaMemcpyAsync(h->field[f] + head * rb, src, (size_t)(first * rb), cudaMemcpyDefault, st));
+    if (first < n)
+      B2RL_CUDA(cudaMemcpyAsync(h->field[f], src + first * rb, (size_t)((n - first) * rb),
+                                cudaMemcpyDefault, st));
+  }
+  B2RL_CUDA(cudaMemcpyAsync(h->scratch_val, prios, (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+  int rc = b2rl_tree_update_impl(h, nullptr, head, h->scratch_val, 0.0f, n, st);
+  if (rc != B2RL_OK) return rc;
+  h->head = (head + n) % h->capacity;
+  h->size = (h->size + n > h->capacity) ? h->capacity : h->size + n;
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(delta >= 0 && delta <= h->size, "delta out of range (0..size)");
+  if (delta == 0) return B2RL_OK;
+  DeviceGuard g(h->device);
+  // oldest record lives at (head - size) mod capacity
+  int64_t tail = h->head - h->size;
+  if (tail < 0) tail += h->capacity;
+  int rc = b2rl_tree_update_impl(h, nullptr, tail, nullptr, 0.0f, delta, (cudaStream_t)stream);
+  if (rc != B2RL_OK) return rc;
+  h->size -= delta;
+  return B2RL_OK;
+}

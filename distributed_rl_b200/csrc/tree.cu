@@ -1,0 +1,321 @@
+// Device-resident sum-tree: bulk build, proportional sampling + IS weights,
+// deterministic batched priority update, stats.
+//
+// Semantics follow the reference's own sum-tree (baseline/sumtree.py) exactly:
+// fp64 nodes, node = fl64(left + right) (Node._reduce :21-27), descent
+// `pos < left ? left : (pos -= left, right)` (Node._find :53-62).  The flat
+// fp32 store the live learners use (baseline/PER.py) agrees with it whenever
+// its own fp32 cumulative sums are exact (tests/golden/tree.npz, dyadic cases).
+//
+// HBM/L2 layout: implicit heap, level k occupies [2^k, 2^(k+1))
+// so both children of a node share one 16-byte aligned pair -> one LDG.128 per
+// level of the descent.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace b2rl {
+
+// ----------------------------------------------------------------------------
+// Bulk build
+// ----------------------------------------------------------------------------
+constexpr int BUILD_CHUNK = 2048;   // leaves per CTA (11 levels resolved in SMEM)
+constexpr int BUILD_THREADS = 256;
+constexpr int BUILD_PER_THREAD = BUILD_CHUNK / 2 / BUILD_THREADS;  // 4
+
+// Each CTA owns leaves [c*2048, (c+1)*2048): converts the fp32 priorities to
+// fp64 leaves, reduces the bottom levels of its subtree in shared memory and
+// writes every node out; its subtree root lands at heap index cap2/2048 + c.
+__global__ void __launch_bounds__(BUILD_THREADS)
+k_build_bottom(const float* __restrict__ prios, int64_t n_valid, double* __restrict__ sum,
+               float* __restrict__ minv, int64_t cap2) {
+  __shared__ double s_sum[BUILD_CHUNK];
+  __shared__ float s_min[BUILD_CHUNK];
+  const int64_t leaf0 = (int64_t)blockIdx.x * BUILD_CHUNK;
+  const int nleaf = (int)min((int64_t)BUILD_CHUNK, cap2 - leaf0);  // cap2 < 2048 -> one CTA
+  for (int i = threadIdx.x; i < nleaf; i += BUILD_THREADS) {
+    const int64_t j = leaf0 + i;
+    const float p = (j < n_valid) ? prios[j] : 0.0f;
+    const float m = (p > 0.0f) ? p : INFINITY;
+    s_sum[i] = (double)p;
+    s_min[i] = m;
+    sum[cap2 + j] = (double)p;
+    minv[cap2 + j] = m;
+  }
+  __syncthreads();
+  int per = 2;  // leaves per node of the level being produced
+  for (int w = nleaf / 2; w >= 1; w >>= 1, per <<= 1) {
+    const int64_t base = (cap2 + leaf0) / per;  // heap index of this CTA's first node on the level
+    double ts[BUILD_PER_THREAD];
+    float tm[BUILD_PER_THREAD];
+    int c = 0;
+    for (int i = threadIdx.x; i < w; i += BUILD_THREADS, ++c) {
+      ts[c] = s_sum[2 * i] + s_sum[2 * i + 1];
+      tm[c] = fminf(s_min[2 * i], s_min[2 * i + 1]);
+    }
+    __syncthreads();
+    c = 0;
+    for (int i = threadIdx.x; i < w; i += BUILD_THREADS, ++c) {
+      s_sum[i] = ts[c];
+      s_min[i] = tm[c];
+      sum[base + i] = ts[c];
+      minv[base + i] = tm[c];
+    }
+    __syncthreads();
+  }
+}
+
+// Levels above the 2048-leaf subtrees: `m` = cap2/2048 nodes on the deepest of
+// them.  One CTA, level-synchronous (at most 12 levels for cap2 = 2^23).
+__global__ void __launch_bounds__(1024)
+k_build_top(double* __restrict__ sum, float* __restrict__ minv, int64_t m) {
+  for (int64_t w = m / 2; w >= 1; w >>= 1) {
+    for (int64_t i = threadIdx.x; i < w; i += blockDim.x) {
+      const int64_t node = w + i;
+      const double2 c = *reinterpret_cast<const double2*>(sum + 2 * node);
+      const float2 mm = *reinterpret_cast<const float2*>(minv + 2 * node);
+      sum[node] = c.x + c.y;
+      minv[node] = fminf(mm.x, mm.y);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sum[0] = 0.0; minv[0] = INFINITY; }
+}
+
+// ----------------------------------------------------------------------------
+// Sampling + importance weights
+// ----------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 128;
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+k_tree_sample(const double* __restrict__ sum, const float* __restrict__ minv, int64_t cap2,
+              int levels, const double* __restrict__ u01, uint64_t seed, uint64_t rng_offset,
+              int64_t n, float n_valid, float beta, int64_t* __restrict__ idx_out,
+              float* __restrict__ prob_out, float* __restrict__ w_out) {
+  const int64_t k = (int64_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x;
+  if (k >= n) return;
+  const double root = sum[1];
+  const double u = u01 ? u01[k] : philox_u01(seed, rng_offset + (uint64_t)k);
+  double pos = __dmul_rn(root, u);  // np.random.uniform(0, root) == root * random_sample()
+  int64_t i = 1;
+  for (int l = 0; l < levels; ++l) {
+    const double2 c = *reinterpret_cast<const double2*>(sum + 2 * i);
+    // Node._find: left iff pos < left.  The `c.y == 0` guard only matters when
+    // pos rounds up to the subtree total (the reference dereferences None there).
+    const bool left = (pos < c.x) || (c.y == 0.0);
+    if (!left) pos = __dsub_rn(pos, c.x);
+    i = 2 * i + (left ? 0 : 1);
+  }
+  const int64_t j = i - cap2;
+  idx_out[k] = j;
+  if (prob_out == nullptr && w_out == nullptr) return;
+  // APE_X/ReplayMemory.py:65-67, baseline/PER.py:98,129-133 — fp32 op by op.
+  const float s32 = (float)root;
+  const float p = (float)sum[i];
+  const float prob = __fdiv_rn(p, s32);
+  if (prob_out) prob_out[k] = prob;
+  if (w_out) {
+    const float w_un = powcr(__fdiv_rn(1.0f, __fmul_rn(n_valid, prob)), beta);
+    const float min_prob = __fdiv_rn(minv[1], s32);
+    const float max_w = powcr(__fmul_rn(n_valid, min_prob), -beta);
+    w_out[k] = __fdiv_rn(w_un, max_w);
+  }
+}
+
+__global__ void k_philox_uniforms(uint64_t seed, uint64_t off, int64_t n, double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = philox_u01(seed, off + (uint64_t)k);
+}
+
+__global__ void k_tree_stats(const double* __restrict__ sum, const float* __restrict__ minv,
+                             float n_valid, float beta, double* __restrict__ out) {
+  const double root = sum[1];
+  const float s32 = (float)root;
+  const float mn = minv[1];
+  out[0] = root;
+  out[1] = (double)mn;
+  out[2] = (double)powcr(__fmul_rn(n_valid, __fdiv_rn(mn, s32)), -beta);
+}
+
+__global__ void k_tree_leaves(const double* __restrict__ sum, int64_t cap2, int64_t start, int64_t n,
+                              float* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = (float)sum[cap2 + start + k];
+}
+
+// ----------------------------------------------------------------------------
+// Batched priority update — deterministic last-writer-wins, no fp atomics.
+//   A  tag[idx[k]] = max(tag, k+1)                     (who is the last writer?)
+//   B  winners write their leaf and mark every ancestor with the side they
+//      come from (bit0 = left child touched, bit1 = right child touched)
+//   C  winners climb; a node expects popc(mark&3) arrivals, and only the LAST
+//      arriver recomputes node = left + right from the (now final) children
+//      and continues upward.
+// tag[] and mark[] return to zero, so the sequence is CUDA-graph replayable.
+// The final tree equals the reference's sequential writes because every
+// Node._reduce recomputes the node from its children (state is path-independent).
+// ----------------------------------------------------------------------------
+constexpr int UPD_THREADS = 256;
+
+__device__ __forceinline__ int64_t upd_index(const int64_t* idx, int64_t ring_start, int64_t capacity,
+                                             int64_t k) {
+  if (idx) return idx[k];
+  int64_t j = ring_start + k;
+  return j >= capacity ? j - capacity : j;
+}
+
+__global__ void __launch_bounds__(UPD_THREADS)
+k_update_tag(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity, int64_t n,
+             uint32_t* __restrict__ tag) {
+  const int64_t k = (int64_t)blockIdx.x * UPD_THREADS + threadIdx.x;
+  if (k >= n) return;
+  const int64_t j = upd_index(idx, ring_start, capacity, k);
+  if (j < 0 || j >= capacity) return;  // out-of-range indices are ignored
+  atomicMax(tag + j, (uint32_t)(k + 1));
+}
+
+__global__ void __launch_bounds__(UPD_THREADS)
+k_update_write(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
+               const float* __restrict__ vals, float const_val, int64_t n,
+               const uint32_t* __restrict__ tag, double* __restrict__ sum, float* __restrict__ minv,
+               int32_t* __restrict__ mark, int64_t cap2, int levels) {
+  const int64_t k = (int64_t)blockIdx.x * UPD_THREADS + threadIdx.x;
+  if (k >= n) return;
+  const int64_t j = upd_index(idx, ring_start, capacity, k);
+  if (j < 0 || j >= capacity) return;
+  if (tag[j] != (uint32_t)(k + 1)) return;  // a later k wrote the same slot
+  const float p = vals ? vals[k] : const_val;
+  int64_t node = cap2 + j;
+  sum[node] = (double)p;
+  minv[node] = (p > 0.0f) ? p : INFINITY;
+  for (int l = 0; l < levels; ++l) {
+    const int bit = (node & 1) ? 2 : 1;
+    node >>= 1;
+    const int old = atomicOr(mark + node, bit);
+    if (old & bit) break;  // another winner below the same child already marks the rest of the path
+  }
+}
+
+__global__ void __launch_bounds__(UPD_THREADS)
+k_update_climb(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity, int64_t n,
+               uint32_t* __restrict__ tag, double* __restrict__ sum, float* __restrict__ minv,
+               int32_t* __restrict__ mark, int64_t cap2, int levels) {
+  const int64_t k = (int64_t)blockIdx.x * UPD_THREADS + threadIdx.x;
+  if (k >= n) return;
+  const int64_t j = upd_index(idx, ring_start, capacity, k);
+  if (j < 0 || j >= capacity) return;
+  if (tag[j] != (uint32_t)(k + 1)) return;
+  tag[j] = 0u;  // self-clean (only the winner touches it in this kernel)
+  int64_t node = cap2 + j;
+  for (int l = 0; l < levels; ++l) {
+    node >>= 1;
+    __threadfence();                               // publish my child before announcing
+    const int old = atomicAdd(mark + node, 4);     // arrivals live above the two side bits
+    if ((old >> 2) + 1 < __popc(old & 3)) return;  // the other touched child arrives later
+    __threadfence();                               // acquire: see the other subtree's writes
+    const double2 c = __ldcg(reinterpret_cast<const double2*>(sum + 2 * node));
+    const float2 m = __ldcg(reinterpret_cast<const float2*>(minv + 2 * node));
+    sum[node] = c.x + c.y;
+    minv[node] = fminf(m.x, m.y);
+    mark[node] = 0;                                // self-clean: nobody else visits this node now
+  }
+}
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// idx_dev == nullptr means the ring range [ring_start, ring_start+n) (mod capacity);
+// vals_dev == nullptr means the constant `const_val`.
+int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_start,
+                          const float* vals_dev, float const_val, int64_t n, cudaStream_t st) {
+  if (n == 0) return B2RL_OK;
+  const unsigned g = grid_for(n, UPD_THREADS);
+  k_update_tag<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag);
+  k_update_write<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, vals_dev, const_val, n,
+                                            h->tag, h->sum, h->minv, h->mark, h->cap2, h->levels);
+  k_update_climb<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag, h->sum,
+                                            h->minv, h->mark, h->cap2, h->levels);
+  count_launch(3);
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 0 && n <= h->capacity, "n out of range");
+  B2RL_REQUIRE(n == 0 || prios_dev != nullptr, "null priorities");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t chunks = (h->cap2 + BUILD_CHUNK - 1) / BUILD_CHUNK;
+  k_build_bottom<<<(unsigned)chunks, BUILD_THREADS, 0, st>>>(prios_dev, n, h->sum, h->minv, h->cap2);
+  count_launch();
+  if (h->cap2 > BUILD_CHUNK) {
+    k_build_top<<<1, 1024, 0, st>>>(h->sum, h->minv, h->cap2 / BUILD_CHUNK);
+    count_launch();
+  }
+  B2RL_CHECK_LAUNCH();
+  h->size = n;
+  h->head = (n == h->capacity) ? 0 : n;
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t seed,
+                                uint64_t rng_offset, int64_t n, float beta, int64_t* idx_out_dev,
+                                float* prob_out_dev, float* w_out_dev, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 0, "negative n");
+  B2RL_REQUIRE(h->size > 0, "sampling from an empty replay");
+  B2RL_REQUIRE(n == 0 || idx_out_dev != nullptr, "null idx_out");
+  if (n == 0) return B2RL_OK;
+  DeviceGuard g(h->device);
+  k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(
+      h->sum, h->minv, h->cap2, h->levels, u01_dev, seed, rng_offset, n, (float)h->size, beta,
+      idx_out_dev, prob_out_dev, w_out_dev);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_philox_uniforms(uint64_t seed, uint64_t rng_offset, int64_t n, double* out_dev,
+                                    void* stream) {
+  B2RL_REQUIRE(n >= 0 && (n == 0 || out_dev), "bad arguments");
+  if (n == 0) return B2RL_OK;
+  k_philox_uniforms<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(seed, rng_offset, n, out_dev);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_tree_update(b2rl_replay* h, const int64_t* idx_dev, const float* vals_dev,
+                                int64_t n, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 0, "negative n");
+  B2RL_REQUIRE(n == 0 || (idx_dev && vals_dev), "null idx/vals");
+  B2RL_REQUIRE(n < (int64_t)0xFFFFFFFFLL, "batch too large");
+  DeviceGuard g(h->device);
+  return b2rl_tree_update_impl(h, idx_dev, 0, vals_dev, 0.0f, n, (cudaStream_t)stream);
+}
+
+extern "C" int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev, void* stream) {
+  B2RL_REQUIRE(h != nullptr && stats_out_dev != nullptr, "null argument");
+  DeviceGuard g(h->device);
+  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->sum, h->minv, (float)h->size, beta, stats_out_dev);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_tree_leaves(b2rl_replay* h, int64_t start, int64_t n, float* out_dev, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(start >= 0 && n >= 0 && start + n <= h->capacity, "range out of bounds");
+  if (n == 0) return B2RL_OK;
+  B2RL_REQUIRE(out_dev != nullptr, "null out");
+  DeviceGuard g(h->device);
+  k_tree_leaves<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->sum, h->cap2, start, n, out_dev);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}

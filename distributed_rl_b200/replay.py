@@ -1,0 +1,310 @@
+"""DeviceReplay — one HBM-resident replay shard (payload SoA + fp64 sum-tree).
+
+Thin, typed wrapper over the C ABI (include/b2rl.h).  All heavy lifting happens
+in the CUDA kernels of libb2rl.so; this file only marshals torch tensors'
+device pointers and the current CUDA stream.  It is the object the reference-
+facing mirrors (per.py: PER / PrioritizedMemory, apex.py: Replay) are built on.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ReplayDesc, check
+
+FRAME_STACK_BYTES = 4 * 84 * 84  # one (4,84,84) uint8 observation, 28 224 B
+
+
+@dataclass(frozen=True)
+class Field:
+    name: str
+    dtype: torch.dtype
+    shape: tuple  # per-slot shape
+
+    @property
+    def nbytes(self) -> int:
+        n = 1
+        for s in self.shape:
+            n *= int(s)
+        return n * torch.empty((), dtype=self.dtype).element_size()
+
+
+# Record layouts of the three learners.
+APEX_FIELDS = (  # [s, a, R_n, s', done, prio]  APE_X/Player.py:252-261
+    Field("state", torch.uint8, (4, 84, 84)),
+    Field("next_state", torch.uint8, (4, 84, 84)),
+    Field("action", torch.int32, ()),
+    Field("reward", torch.float32, ()),
+    Field("done", torch.uint8, ()),
+)
+
+
+def r2d2_fields(T: int = 80, hidden: int = 512):
+    """[(h0,h1), (s,a,r) x T, done, prio]  R2D2/ReplayMemory.py:70-88."""
+    return (
+        Field("state", torch.uint8, (T, 4, 84, 84)),
+        Field("action", torch.int32, (T,)),
+        Field("reward", torch.float32, (T,)),
+        Field("h0", torch.float32, (hidden,)),
+        Field("h1", torch.float32, (hidden,)),
+        Field("notdone", torch.float32, ()),
+    )
+
+
+def impala_fields(T: int = 20):
+    """(s[T+1], a[T], mu[T], r[T], done)  IMPALA/ReplayMemory.py:34-43."""
+    return (
+        Field("state", torch.uint8, (T + 1, 4 * 84 * 84)),
+        Field("action", torch.int32, (T,)),
+        Field("mu", torch.float32, (T,)),
+        Field("reward", torch.float32, (T,)),
+        Field("done", torch.float32, ()),
+    )
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _CudaView:
+    """Expose library-owned device memory to torch via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+        self._owner = owner
+
+
+_TYPESTR = {torch.uint8: "|u1", torch.int32: "<i4", torch.int64: "<i8", torch.float32: "<f4",
+            torch.float64: "<f8", torch.int8: "|i1", torch.int16: "<i2", torch.float16: "<f2"}
+
+
+class DeviceReplay:
+    def __init__(self, capacity: int, fields: Sequence[Field] = APEX_FIELDS, device="cuda:0"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.B2RLError("DeviceReplay lives in GPU HBM; there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.fields = tuple(fields)
+        if len(self.fields) > _lib.MAX_FIELDS:
+            raise ValueError("too many payload fields")
+        self.capacity = int(capacity)
+        d = ReplayDesc()
+        d.capacity = self.capacity
+        d.n_fields = len(self.fields)
+        d.device = self.device.index
+        for i, f in enumerate(self.fields):
+            d.field_bytes[i] = f.nbytes
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+        h = C.c_void_p()
+        check(self.lib.b2rl_replay_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self._rng_offset = 0
+        self.seed = 1234
+
+    # -- bookkeeping -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.b2rl_replay_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _sizes(self):
+        s, c, hd = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.lib.b2rl_replay_size(self._h, C.byref(s), C.byref(c), C.byref(hd)))
+        return s.value, c.value, hd.value
+
+    def __len__(self) -> int:
+        return self._sizes()[0]
+
+    @property
+    def head(self) -> int:
+        return self._sizes()[2]
+
+    def _st(self) -> int:
+        return _stream_ptr(self.device)
+
+    def field_view(self, name_or_idx) -> torch.Tensor:
+        """Zero-copy torch view (capacity, *shape) of a library-owned payload field."""
+        i = name_or_idx if isinstance(name_or_idx, int) else [f.name for f in self.fields].index(name_or_idx)
+        f = self.fields[i]
+        p = C.c_void_p()
+        check(self.lib.b2rl_replay_field_ptr(self._h, i, C.byref(p)))
+        view = _CudaView(p.value, (self.capacity,) + tuple(f.shape), _TYPESTR[f.dtype], self)
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(view, device=self.device)
+
+    # -- ingest ----------------------------------------------------------------
+    def push(self, fields: Sequence, priorities) -> None:
+        """fields[i]: tensor / ndarray (n, *shape_i), host (pinned preferred) or device."""
+        keep = []
+        ptrs = (C.c_void_p * _lib.MAX_FIELDS)()
+        n = None
+        for i, (f, x) in enumerate(zip(self.fields, fields)):
+            if x is None:
+                ptrs[i] = None
+                continue
+            t = torch.as_tensor(x)
+            if t.dtype != f.dtype:
+                t = t.to(f.dtype)
+            t = t.contiguous()
+            if n is None:
+                n = t.shape[0]
+            assert t.shape[0] == n and t.numel() * t.element_size() == n * f.nbytes, f"bad shape for {f.name}"
+            keep.append(t)
+            ptrs[i] = t.data_ptr()
+        pr = torch.as_tensor(priorities).to(torch.float32).contiguous()
+        if n is None:
+            n = pr.shape[0]
+        assert pr.numel() == n
+        keep.append(pr)
+        check(self.lib.b2rl_replay_push(self._h, ptrs, pr.data_ptr(), n, self._st()))
+        # host buffers must outlive the async copies on this stream
+        if any(not t.is_cuda and not t.is_pinned() for t in keep):
+            pass  # pageable memory: cudaMemcpyAsync already staged it synchronously
+        else:
+            self._inflight = keep
+
+    def evict(self, delta: int) -> None:
+        check(self.lib.b2rl_replay_evict(self._h, int(delta), self._st()))
+
+    def fill_hash(self, n: int, seed: int = 0xB200) -> None:
+        check(self.lib.b2rl_replay_fill_hash(self._h, int(n), int(seed) & 0xFFFFFFFF, self._st()))
+
+    # -- tree ------------------------------------------------------------------
+    def build(self, priorities: torch.Tensor) -> None:
+        p = priorities.to(device=self.device, dtype=torch.float32).contiguous()
+        check(self.lib.b2rl_tree_build(self._h, p.data_ptr(), p.numel(), self._st()))
+
+    def sample(self, n: int, beta: float = 0.4, u01: torch.Tensor | None = None,
+               want_prob: bool = True, out=None):
+        """-> (idx int64[n], prob fp32[n], weight fp32[n]) on the device."""
+        if out is None:
+            idx = torch.empty(n, dtype=torch.int64, device=self.device)
+            prob = torch.empty(n, dtype=torch.float32, device=self.device) if want_prob else None
+            w = torch.empty(n, dtype=torch.float32, device=self.device)
+        else:
+            idx, prob, w = out
+        if u01 is not None:
+            u01 = u01.to(device=self.device, dtype=torch.float64).contiguous()
+            assert u01.numel() == n
+            up = u01.data_ptr()
+        else:
+            up = None
+        check(self.lib.b2rl_tree_sample(self._h, up, self.seed, self._rng_offset, n, float(beta),
+                                        idx.data_ptr(), prob.data_ptr() if prob is not None else None,
+                                        w.data_ptr(), self._st()))
+        if u01 is None:
+            self._rng_offset += n
+        return idx, prob, w
+
+    def philox_uniforms(self, seed: int, offset: int, n: int) -> torch.Tensor:
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        check(self.lib.b2rl_philox_uniforms(seed, offset, n, out.data_ptr(), self._st()))
+        return out
+
+    def update(self, idx: torch.Tensor, vals: torch.Tensor) -> None:
+        idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+        vals = vals.to(device=self.device, dtype=torch.float32).contiguous()
+        assert idx.numel() == vals.numel()
+        check(self.lib.b2rl_tree_update(self._h, idx.data_ptr(), vals.data_ptr(), idx.numel(), self._st()))
+
+    def stats(self, beta: float = 0.4) -> torch.Tensor:
+        """device tensor fp64[3] = {sum(p), min p, max IS weight}."""
+        out = torch.empty(3, dtype=torch.float64, device=self.device)
+        check(self.lib.b2rl_tree_stats(self._h, float(beta), out.data_ptr(), self._st()))
+        return out
+
+    def priorities(self, start: int = 0, n: int | None = None) -> torch.Tensor:
+        n = self.capacity - start if n is None else n
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        check(self.lib.b2rl_tree_leaves(self._h, start, n, out.data_ptr(), self._st()))
+        return out
+
+    # -- gather ----------------------------------------------------------------
+    def alloc_batch(self, n: int, names: Sequence[str] | None = None):
+        names = [f.name for f in self.fields] if names is None else list(names)
+        return {f.name: torch.empty((n,) + tuple(f.shape), dtype=f.dtype, device=self.device)
+                for f in self.fields if f.name in names}
+
+    def gather(self, idx: torch.Tensor, out: dict | None = None) -> dict:
+        n = idx.numel()
+        if out is None:
+            out = self.alloc_batch(n)
+        ptrs = (C.c_void_p * _lib.MAX_FIELDS)()
+        for i, f in enumerate(self.fields):
+            t = out.get(f.name)
+            ptrs[i] = t.data_ptr() if t is not None else None
+        check(self.lib.b2rl_replay_gather(self._h, idx.data_ptr(), n, ptrs, self._st()))
+        return out
+
+
+# ---- stateless target kernels -------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def apex_target(q_s, qn_online, qn_target, action, reward, notdone, weight, gamma_n, alpha,
+                want_grad=True, out=None):
+    """APE_X/Learner.py:85-121 in one launch.  All inputs device tensors."""
+    lib = _lib.load()
+    B, A = q_s.shape
+    dev = q_s.device
+    if out is None:
+        out = {"target": torch.empty(B, device=dev), "td": torch.empty(B, device=dev),
+               "prio": torch.empty(B, device=dev),
+               "grad_q": torch.empty(B, A, device=dev) if want_grad else None,
+               "scalars": torch.empty(3, device=dev)}
+    action = action.to(torch.int64)
+    for t in (q_s, qn_online, qn_target, action, reward, notdone, weight):
+        assert t.is_cuda and t.is_contiguous()
+    check(lib.b2rl_apex_target(_p(q_s), _p(qn_online), _p(qn_target), _p(action), _p(reward), _p(notdone),
+                               _p(weight), B, A, float(np.float32(gamma_n)), float(alpha),
+                               _p(out["target"]), _p(out["td"]), _p(out["prio"]), _p(out.get("grad_q")),
+                               _p(out["scalars"]), _stream_ptr(dev)))
+    return out
+
+
+def r2d2_target(q, q_target, action, reward, notdone, weight, n_step, gamma, alpha, rescale=True,
+                want_grad=True):
+    """R2D2/Learner.py:110-198 in one launch (+ a 1-thread finisher for the scalars)."""
+    lib = _lib.load()
+    L, B, A = q.shape
+    dev = q.device
+    out = {"target": torch.empty(L - 1, B, device=dev), "td": torch.empty(L - 1, B, device=dev),
+           "prio": torch.empty(B, device=dev),
+           "grad_q": torch.empty(L, B, A, device=dev) if want_grad else None,
+           "scalars": torch.empty(2, device=dev)}
+    action = action.to(torch.int64).contiguous()
+    check(lib.b2rl_r2d2_target(_p(q), _p(q_target), _p(action), _p(reward), _p(notdone), _p(weight),
+                               L, B, A, int(n_step), float(gamma), float(alpha), int(bool(rescale)),
+                               _p(out["target"]), _p(out["td"]), _p(out["prio"]), _p(out["grad_q"]),
+                               _p(out["scalars"]), _stream_ptr(dev)))
+    return out
+
+
+def vtrace(pi_a, mu_a, value, bootstrap, reward, gamma, c_lambda, c_bar, p_bar):
+    """IMPALA/Learner.py:141-215 in one launch.  (T, B) time-major."""
+    lib = _lib.load()
+    T, B = value.shape
+    dev = value.device
+    vt = torch.empty(T, B, device=dev)
+    adv = torch.empty(T, B, device=dev)
+    check(lib.b2rl_vtrace(_p(pi_a), _p(mu_a), _p(value), _p(bootstrap), _p(reward), T, B,
+                          float(np.float32(gamma)), float(c_lambda), float(c_bar), float(p_bar),
+                          _p(vt), _p(adv), _stream_ptr(dev)))
+    return vt, adv

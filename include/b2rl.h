@@ -1,0 +1,185 @@
+/* b2rl.h — C ABI of the B200-native learner-side replay path.
+ *
+ * The reference (seungju-k1m/Distributed_RL) is pure Python and defines no
+ * FFI of its own; its boundary for this path is three duck-typed Python
+ * surfaces.  Every entry point below therefore cites the
+ * reference *Python* interface it replaces (paths relative to the reference
+ * root).  The Python mirrors in distributed_rl_b200/ bind these with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every function returns 0 on success, <0 on error; the message is
+ *     available (per thread) from b2rl_last_error().
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *     and is asynchronous w.r.t. the host unless stated otherwise.
+ *   - pointers named *_dev are device pointers owned by the caller (e.g.
+ *     torch tensors' data_ptr()); the library never frees them.
+ *   - the sum-tree and the payload arrays are owned by the handle and freed
+ *     by b2rl_replay_destroy().
+ *   - one producer + one consumer thread may use a handle concurrently as
+ *     long as they enqueue on the same stream (stream order replaces the
+ *     reference's `lock` flag handshake, APE_X/ReplayMemory.py:151-160).
+ */
+#ifndef B2RL_H_
+#define B2RL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2RL_MAX_FIELDS 8
+#define B2RL_OK 0
+#define B2RL_ERR_INVALID (-1)
+#define B2RL_ERR_CUDA (-2)
+#define B2RL_ERR_NOMEM (-3)
+
+typedef struct b2rl_replay b2rl_replay; /* opaque */
+
+/* One replay shard: a ring of `capacity` slots, `n_fields` SoA payload arrays
+ * (field f holds capacity x field_bytes[f] bytes) and an fp64 sum-tree + fp32
+ * min-tree over the slot priorities.
+ * Replaces the storage of baseline/PER.py:48-66 (`memory` list of pickled
+ * records + `Tree.prior_torch`) and baseline/utils.py:328-333
+ * (PrioritizedMemory: CompressedDeque + SumTree). */
+typedef struct {
+  int64_t capacity;                      /* slots; the tree is padded to 2^k */
+  int32_t n_fields;                      /* 0..B2RL_MAX_FIELDS               */
+  int32_t device;                        /* CUDA device ordinal              */
+  int64_t field_bytes[B2RL_MAX_FIELDS];  /* bytes per slot of each field     */
+} b2rl_replay_desc;
+
+const char* b2rl_last_error(void);
+int b2rl_version(void);
+
+/* PER.__init__ (baseline/PER.py:49-66), PrioritizedMemory.__init__
+ * (baseline/utils.py:329-332). */
+int b2rl_replay_create(const b2rl_replay_desc* desc, b2rl_replay** out);
+int b2rl_replay_destroy(b2rl_replay* h);
+
+/* PER.__len__ (baseline/PER.py:80-81): number of valid slots, capacity, and
+ * the ring head (next slot to be written). Host-side, no sync. */
+int b2rl_replay_size(const b2rl_replay* h, int64_t* size, int64_t* capacity, int64_t* head);
+
+/* Device base pointer of payload field f (capacity x field_bytes[f] bytes). */
+int b2rl_replay_field_ptr(const b2rl_replay* h, int32_t field, void** ptr_dev);
+
+/* PER.push (baseline/PER.py:69-75) / PrioritizedMemory.push
+ * (baseline/utils.py:334-337): append n records.  fields_src[f] points to
+ * n x field_bytes[f] contiguous bytes (host — ideally pinned — or device;
+ * copied with cudaMemcpyDefault), prios to n fp32 priorities (same rule).
+ * Slots are written at the ring head; when the ring is full the oldest slots
+ * are overwritten (FIFO, as PER.remove_to_fit :118-127 drops them — but slot
+ * ids stay stable instead of being renumbered).  Leaves and their root paths
+ * are refreshed in the same call.  n <= capacity. */
+int b2rl_replay_push(b2rl_replay* h, const void* const* fields_src, const float* prios,
+                     int64_t n, void* stream);
+
+/* PER.remove_to_fit (baseline/PER.py:118-127): drop the `delta` oldest
+ * records (priority := 0 so they can never be sampled; size -= delta). */
+int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream);
+
+/* Benchmark / property-test helper (no reference counterpart): fill slots
+ * [0, n) of every field with the counter hash documented in DESIGN.md §4
+ * (word w of slot s of field f = lowbias32(seed ^ f*0x9E3779B9 ^ s*2654435761
+ * ^ w*2246822519)) and mark them valid.  Priorities are NOT touched: follow
+ * with b2rl_tree_build(). */
+int b2rl_replay_fill_hash(b2rl_replay* h, int64_t n, uint32_t seed, void* stream);
+
+/* Bulk (re)build: priorities of slots [0, n) := prios_dev[0..n), the rest 0,
+ * then every internal node is recomputed (node = left + right in fp64, as
+ * baseline/sumtree.py Node._reduce :21-27).  State equals
+ * SumTree.extend(prios) (:97-99) / Tree.push (baseline/PER.py:22-28). */
+int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n, void* stream);
+
+/* PER.sample (baseline/PER.py:92-116) + the IS-weight lines of
+ * APE_X/ReplayMemory.py:65-67 and PER.max_weight (:129-133), with the
+ * descent rule of SumTree.prioritized_sample / Node._find
+ * (baseline/sumtree.py:53-62,128-140): pos = root*u; at each node
+ * `pos < left ? left : (pos -= left, right)`.
+ *   u01_dev   n fp64 uniforms in [0,1) on the device, or NULL to draw them
+ *             from Philox4x32-10 (seed, counter = rng_offset + k)
+ *   idx_out   int64[n]  sampled slot ids (with replacement)
+ *   prob_out  fp32[n]   p_i / sum(p)               (may be NULL)
+ *   w_out     fp32[n]   (1/(N*prob))^beta / max_w  (may be NULL)
+ * Sampling from an empty tree is an error. */
+int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t seed, uint64_t rng_offset,
+                     int64_t n, float beta, int64_t* idx_out_dev, float* prob_out_dev,
+                     float* w_out_dev, void* stream);
+
+/* The uniforms b2rl_tree_sample would draw for (seed, rng_offset) — lets a
+ * test replay a device-RNG run through the oracle. */
+int b2rl_philox_uniforms(uint64_t seed, uint64_t rng_offset, int64_t n, double* out_dev,
+                         void* stream);
+
+/* PER.update (baseline/PER.py:83-90 -> Tree.update :36-42) and
+ * PrioritizedMemory.update_priorities (baseline/utils.py:347-350): set
+ * priority[idx[k]] = vals[k] for k = 0..n-1 in order — for a duplicated index
+ * the LAST occurrence wins — and refresh the touched root paths.
+ * Deterministic (no floating-point atomics). */
+int b2rl_tree_update(b2rl_replay* h, const int64_t* idx_dev, const float* vals_dev, int64_t n,
+                     void* stream);
+
+/* PrioritizedMemory.total_prios (baseline/utils.py:359-360) and
+ * PER.max_weight (baseline/PER.py:129-133).  stats_out_dev receives 3
+ * doubles: {sum(p), min valid p, max IS weight for `beta`}. */
+int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev, void* stream);
+
+/* Tree.prior_torch (baseline/PER.py:17) read-back: priorities of slots
+ * [start, start+n) as fp32. */
+int b2rl_tree_leaves(b2rl_replay* h, int64_t start, int64_t n, float* out_dev, void* stream);
+
+/* Minibatch assembly of Replay.buffer (APE_X/ReplayMemory.py:61-116,
+ * R2D2/ReplayMemory.py:53-122, IMPALA/ReplayMemory.py:30-54): for every
+ * field f with out_fields[f] != NULL copy row idx[k] to out_fields[f] + k *
+ * field_bytes[f].  Rows that are multiples of 16 B go HBM -> SMEM -> HBM with
+ * bulk async copies (TMA); the rest through a vectorised byte kernel. */
+int b2rl_replay_gather(b2rl_replay* h, const int64_t* idx_dev, int64_t n,
+                       void* const* out_fields_dev, void* stream);
+
+/* Learner.train target section, Ape-X (APE_X/Learner.py:85-121):
+ *   a* = argmax_a qn_online[b,:];  y = r + gamma_n * qn_target[b,a*] * notdone
+ *   d = clamp(y - q_s[b,action[b]], -1, 1);  prio = (|d| + 1e-7)^alpha
+ *   loss = 0.5 * mean(w * d^2);  grad_q = dLoss/dq_s  (dense B x A)
+ * q_* are (B, A) fp32 row-major; action int64[B]; reward/notdone/weight
+ * fp32[B].  scalars_out_dev receives 3 floats {loss, mean(y), mean(w)}.
+ * Any output pointer may be NULL. */
+int b2rl_apex_target(const float* q_s_dev, const float* qn_online_dev, const float* qn_target_dev,
+                     const int64_t* action_dev, const float* reward_dev, const float* notdone_dev,
+                     const float* weight_dev, int32_t B, int32_t A, float gamma_n, float alpha,
+                     float* target_out_dev, float* td_out_dev, float* prio_out_dev,
+                     float* grad_q_out_dev, float* scalars_out_dev, void* stream);
+
+/* Learner.train target section, R2D2 (R2D2/Learner.py:110-198) with
+ * value_transform / value_inv_transform (:22-35).  Time-major layouts:
+ * q, q_target (L, B, A); action int64 (L-1, B); reward fp32 (L-1, B);
+ * notdone fp64-valued but passed as fp32[B] (0/1); weight fp32[B].
+ * Outputs: target, td (L-1, B); prio fp32[B] =
+ * (0.9 max_t|td| + 0.1 mean_t|td|)^alpha; grad_q (L, B, A);
+ * scalars {loss, mean q(s,a)}. */
+int b2rl_r2d2_target(const float* q_dev, const float* q_target_dev, const int64_t* action_dev,
+                     const float* reward_dev, const float* notdone_dev, const float* weight_dev,
+                     int32_t L, int32_t B, int32_t A, int32_t n_step, double gamma, float alpha,
+                     int32_t use_rescaling, float* target_out_dev, float* td_out_dev,
+                     float* prio_out_dev, float* grad_q_out_dev, float* scalars_out_dev,
+                     void* stream);
+
+/* V-trace of IMPALA (IMPALA/Learner.py:141-215), (T, B) time-major fp32:
+ * pi_a = learner prob of the taken action, mu_a = behaviour prob, value =
+ * V(s_t), bootstrap[B] = V(s_T) * done, reward.  Outputs vtarget (T, B)
+ * (:202) and advantage (T, B) (:207-212). */
+int b2rl_vtrace(const float* pi_a_dev, const float* mu_a_dev, const float* value_dev,
+                const float* bootstrap_dev, const float* reward_dev, int32_t T, int32_t B,
+                float gamma, float c_lambda, float c_bar, float p_bar, float* vtarget_out_dev,
+                float* advantage_out_dev, void* stream);
+
+/* Number of kernels this library has launched in this process (bench.py's
+ * `gpu_launches`). */
+int64_t b2rl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RL_H_ */

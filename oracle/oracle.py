@@ -66,7 +66,8 @@ class SumTreeOracle:
         self.sum[:] = 0.0
         self.min[:] = np.inf
         self.sum[self.cap:self.cap + n] = p.astype(F64)
-        self.min[self.cap:self.cap + n] = p.astype(F32)
+        p32 = p.astype(F32)
+        self.min[self.cap:self.cap + n] = np.where(p32 > 0, p32, F32(np.inf))  # p == 0 <=> empty slot
         lvl = self.cap // 2
         while lvl >= 1:
             i = np.arange(lvl, 2 * lvl)
@@ -83,11 +84,13 @@ class SumTreeOracle:
         return self.min[1]
 
     def find(self, pos: float) -> int:
-        """Node._find (:53-62): `pos < left ? left : (pos -= left, right)`."""
+        """Node._find (:53-62): `pos < left ? left : (pos -= left, right)`.
+        The `right == 0` guard only acts when pos has rounded up to the subtree
+        total, where the reference dereferences a None child and raises."""
         i = 1
         while i < self.cap:
             left = self.sum[2 * i]
-            if pos < left:
+            if pos < left or self.sum[2 * i + 1] == 0.0:
                 i = 2 * i
             else:
                 pos = pos - left
@@ -101,8 +104,7 @@ class SumTreeOracle:
         root = self.sum[1]
         idx = np.empty(u01.shape[0], np.int64)
         for k in range(u01.shape[0]):
-            j = self.find(root * u01[k])
-            idx[k] = min(j, max(self.size - 1, 0))  # reference raises past the last leaf
+            idx[k] = self.find(root * u01[k])
         return idx, self.sum[self.cap + idx].copy()
 
     def update(self, idx, vals) -> None:
@@ -113,7 +115,7 @@ class SumTreeOracle:
         vals = np.asarray(vals)
         for j, v in zip(idx, vals):
             self.sum[self.cap + j] = F64(v)
-            self.min[self.cap + j] = F32(v)
+            self.min[self.cap + j] = F32(v) if F32(v) > 0 else F32(np.inf)
         touched = np.unique(idx + self.cap)
         while touched.size and touched[0] > 1:
             touched = np.unique(touched // 2)
@@ -317,3 +319,76 @@ def vtrace(pi_a, mu_a, value, bootstrap, reward,
     pt = np.minimum(F32(p_bar), ratio)
     adv = ((atarget - value).astype(F32) * pt).astype(F32)
     return vtarget, adv, ratio
+
+
+# --------------------------------------------------------------------------- #
+# Synthetic payload hash + device RNG (no reference counterpart; restated so    #
+# that full-size GPU runs can be verified without materialising them on host)   #
+# --------------------------------------------------------------------------- #
+def lowbias32(x: np.ndarray) -> np.ndarray:
+    x = np.asarray(x, np.uint32).copy()
+    x ^= x >> np.uint32(16); x *= np.uint32(0x7FEB352D)
+    x ^= x >> np.uint32(15); x *= np.uint32(0x846CA68B)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def hash_rows(field_index: int, slots: np.ndarray, row_bytes: int, seed: int) -> np.ndarray:
+    """Bytes that b2rl_replay_fill_hash writes into rows `slots` of field `field_index`."""
+    slots = np.asarray(slots, np.int64)
+    words = (row_bytes + 3) // 4
+    with np.errstate(over="ignore"):
+        s = (slots.astype(np.uint32) * np.uint32(2654435761))[:, None]
+        w = (np.arange(words, dtype=np.uint32) * np.uint32(2246822519))[None, :]
+        fs = np.uint32((field_index * 0x9E3779B9) & 0xFFFFFFFF)
+        v = lowbias32(np.uint32(seed & 0xFFFFFFFF) ^ fs ^ s ^ w)
+    b = v.astype("<u4").view(np.uint8).reshape(len(slots), words * 4)
+    return b[:, :row_bytes]
+
+
+def philox_u01(seed: int, offset: int, n: int) -> np.ndarray:
+    """Philox4x32-10 uniforms as k_tree_sample draws them: counter (ctr,0), key = seed."""
+    ctr = np.arange(offset, offset + n, dtype=np.uint64)
+    c0 = (ctr & np.uint64(0xFFFFFFFF)); c1 = (ctr >> np.uint64(32))
+    c2 = np.zeros(n, np.uint64); c3 = np.zeros(n, np.uint64)
+    k0 = np.uint64(seed & 0xFFFFFFFF); k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c0; p1 = M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ k0
+        n1 = p1 & mask
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ k1
+        n3 = p0 & mask
+        c0, c1, c2, c3 = n0 & mask, n1, n2 & mask, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    x = (c1 << np.uint64(32)) | c0
+    return (x & np.uint64((1 << 53) - 1)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+class RingModel:
+    """Host model of the device ring (b2rl_replay_push / _evict): stable slot ids,
+    FIFO overwrite — the idiomatic replacement of PER.remove_to_fit's renumbering
+    (baseline/PER.py:118-127)."""
+
+    def __init__(self, capacity: int):
+        self.capacity = capacity
+        self.prios = np.zeros(capacity, F32)
+        self.size = 0
+        self.head = 0
+
+    def push(self, prios):
+        prios = np.asarray(prios, F32)
+        slots = (self.head + np.arange(len(prios))) % self.capacity
+        self.prios[slots] = prios
+        self.head = int((self.head + len(prios)) % self.capacity)
+        self.size = min(self.capacity, self.size + len(prios))
+        return slots
+
+    def evict(self, delta):
+        tail = (self.head - self.size) % self.capacity
+        slots = (tail + np.arange(delta)) % self.capacity
+        self.prios[slots] = 0
+        self.size -= delta
+        return slots
