@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — learner transitions/s for the Ape-X hot path (sample + gather +
+target + priority update, inside a full learner step) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): Ape-X DQN, 2^20-slot
+device-resident sum-tree per GPU, synthetic (4,84,84) uint8 frame stacks (59.2 GB
+payload per GPU), batch 512 per GPU.  One "step" = one learner step:
+  tree sample (512) -> IS weights -> TMA gather of s, s', a, r, done ->
+  Q(s), Q(s'), Qbar(s') -> fused double-DQN n-step target / clipped TD /
+  priority / dLoss/dQ -> backward -> centered RMSprop -> tree priority write-back
+N > 1: one process per GPU, replay sharded (2^20 slots each, weak scaling),
+NCCL all-reduce of the gradients (AVG) and of the max IS weight (MAX) — the
+only inter-GPU traffic.
+
+`value` = transitions/s with everything resident in HBM, the whole step replayed
+as one CUDA graph.  `e2e` = the same loop through the public Python API with
+HOST buffers: every step ingests 512 new transitions from pinned host memory
+(Replay.push_arrays -> b2rl_replay_push) and reads the step's scalars back.
+
+--impl reference times the CPU port of the reference learner loop
+(oracle/cpu_learner.py; the reference is pure Python and /root/reference does not
+exist on the GPU box) on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "learner transitions/sec (sample+target+prio-update)"
+UNIT = "transitions/s"
+ALG_BYTES_PER_TRANSITION_GATHER = 2 * 28224 + 4 + 4 + 1   # 56 457 B read per transition
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=20, help="log2 of replay slots per GPU")
+    ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- #
+# clocks                                                                        #
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------- #
+# reference arm / cpu baseline                                                  #
+# --------------------------------------------------------------------------- #
+def run_cpu_port(n_slots, batch, steps, warmup):
+    """`steps` train steps of the CPU port, sampled/assembled `m` at a time like the reference."""
+    import torch
+    from oracle.cpu_learner import CpuApexLearner
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = max(1, min(16, steps))
+    L = CpuApexLearner(n_slots, batch, m=m, pool=2048, threads=cores)
+    cycles = max(1, (steps + m - 1) // m)
+    for _ in range(max(0, (warmup + m - 1) // m)):
+        L.cycle()
+    tot_t, tot_n, parts = 0.0, 0, {"t_buffer": 0.0, "t_train": 0.0, "t_update": 0.0}
+    for _ in range(cycles):
+        r = L.cycle()
+        tot_t += r["t_total"]; tot_n += r["transitions"]
+        for k in parts:
+            parts[k] += r[k]
+    return {"value": tot_n / tot_t, "seconds": tot_t, "transitions": tot_n, "cores": cores, "m": m,
+            "cycles": cycles, "parts": {k: v / cycles for k, v in parts.items()}}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 1 << args.log2n
+    steps = min(args.steps, 16)          # bounded sample: <= 16 train steps of 512 on the host cores
+    warm = min(args.warmup, 2)
+    r = run_cpu_port(n, args.batch, steps, warm)
+    sample = (f"{r['cycles']} cycle(s) of {r['m']} train steps x batch {args.batch} at N=2^{args.log2n} "
+              f"priorities (payload pool of 2048 pickled records), after {warm} warm-up step(s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["cycles"] * r["m"], "warmup": warm, "ms_per_step": 1e3 * r["seconds"] / (r["cycles"] * r["m"]),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+                         "parts_s_per_cycle": r["parts"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"Ape-X DQN learner step, 2^{args.log2n}-slot device sum-tree per GPU, synthetic (4,84,84) "
+                        f"uint8 frame stacks, batch={args.batch} per GPU (BASELINE.json configs[1])",
+            "slots_per_gpu": 1 << args.log2n, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "record_bytes": ALG_BYTES_PER_TRANSITION_GATHER,
+            "parallelism": f"replay-sharded dp{world}" if world > 1 else "single GPU",
+            "l2": "inputs >> L2: every step gathers random rows of a 59 GB payload (no L2 flush needed)",
+            "network": "dueling DQN of cfg/ape_x.json in PyTorch (fp32, cuDNN TF32 convs = torch defaults)"}
+
+
+# --------------------------------------------------------------------------- #
+# our arm                                                                       #
+# --------------------------------------------------------------------------- #
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from distributed_rl_b200 import _lib, replay as R
+    from distributed_rl_b200.apex import ApexConfig, Learner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    N, B = 1 << args.log2n, args.batch
+    cfg = ApexConfig(BATCHSIZE=B, REPLAY_MEMORY_LEN=N, BUFFER_SIZE=0, LEARNER_DEVICE=str(dev))
+    torch.manual_seed(0)
+    learner = Learner(cfg, connect=None, start_replay=False)
+    if world > 1:   # identical initial weights on every rank
+        for p in list(learner.model.parameters()) + list(learner.target_model.parameters()):
+            dist.broadcast(p.data, 0)
+        learner.enable_data_parallel()
+    store = learner.memory.store
+    # ---- pre-fill: synthetic frames by counter hash, typed scalars, priorities ----
+    store.fill_hash(N, seed=0xB200 + rank)
+    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 1 + rank)
+    store.field_view("action").copy_(torch.randint(0, cfg.ACTION_SIZE, (N,), device=dev, generator=g, dtype=torch.int32))
+    store.field_view("reward").copy_(torch.randn(N, device=dev, generator=g).clamp_(-1, 1))
+    store.field_view("done").copy_((torch.rand(N, device=dev, generator=g) < 0.02).to(torch.uint8))
+    prios = (torch.randn(N, device=dev, generator=g).abs().clamp(max=1) + 1e-7) ** cfg.ALPHA
+    store.build(prios)
+    store.seed(1234 + rank, 0)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: the whole step as one CUDA graph --------------------------
+    use_graph = not args.no_graph
+    for _ in range(max(3, args.warmup)):     # first call builds (3 eager warm-ups + capture)
+        learner.fused_step(use_graph=use_graph)
+    per_step_launches = learner.launches_per_step
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = learner.fused_step(use_graph=use_graph)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clock_info = clocks.stop() if clocks else None
+    value = B * world * args.steps / (ms / 1e3)
+    scal = out["scalars"].tolist()
+
+    # ---- dominant hand-written kernel: the TMA gather, timed alone with CUDA events -------
+    reps = 20
+    idxs = [store.sample(B, beta=cfg.BETA, want_prob=False)[0] for _ in range(reps)]
+    outb = store.alloc_batch(B)
+    for i in range(3):
+        store.gather(idxs[i], outb)
+    torch.cuda.synchronize()
+    gg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gg):
+        for i in range(reps):
+            store.gather(idxs[i], outb)     # big-row bulk kernel + one small kernel per scalar field
+    gg.replay(); torch.cuda.synchronize()
+    g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+    g0.record(); gg.replay(); g1.record(); torch.cuda.synchronize()
+    gather_us = g0.elapsed_time(g1) * 1e3 / reps
+    # subtract nothing: the 3 small-field kernels are part of the gather of one transition
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ALG_BYTES_PER_TRANSITION_GATHER * B / (gather_us * 1e-6) / 1e9
+    roofline = {"kernel": "k_gather_bulk (+3 k_gather_small) — TMA bulk gather of one batch", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)" if peaks else "fallback 6650",
+                "traffic": None, "launch_us": gather_us, "algorithmic_bytes_per_launch": ALG_BYTES_PER_TRANSITION_GATHER * B,
+                "note": "a gather is a copy: HBM traffic = 2x the algorithmic (read-only) bytes, so frac <= 0.5 "
+                        "until the gather is fused into its consumer"}
+    prof = os.path.join(REPO, "profiles", "r01_gather_traffic.json")
+    if os.path.isfile(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: public API, host buffers in, scalars out -----------------------------------
+    pin = lambda t: t.pin_memory()
+    rng = np.random.default_rng(7 + rank)
+    hs = pin(torch.from_numpy(rng.integers(0, 256, size=(B, 4, 84, 84), dtype=np.uint8)))
+    hns = pin(torch.from_numpy(rng.integers(0, 256, size=(B, 4, 84, 84), dtype=np.uint8)))
+    ha = pin(torch.from_numpy(rng.integers(0, 6, size=B).astype(np.int32)))
+    hr = pin(torch.from_numpy(np.clip(rng.standard_normal(B), -1, 1).astype(np.float32)))
+    hd = pin(torch.from_numpy((rng.random(B) < 0.02).astype(np.uint8)))
+    hp = pin(torch.ones(B, dtype=torch.float32))
+    h2d = sum(t.numel() * t.element_size() for t in (hs, hns, ha, hr, hd, hp))
+    host_scal = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        learner.memory.push_arrays(hs, hns, ha, hr, hd, hp)       # H2D of 512 new transitions
+        o = learner.fused_step(use_graph=use_graph)
+        host_scal.copy_(o["scalars"], non_blocking=False)          # D2H + sync: loss, mean target, mean w
+        return host_scal
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    k2 = max(10, args.steps // 4)
+    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(k2):
+        e2e_step()
+    s1.record()
+    barrier()
+    ms2 = s0.elapsed_time(s1)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+    e2e = {"value": B * world * k2 / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 12, "steps": k2,
+           "what": "Replay.push_arrays(512 new transitions from pinned host) + Learner.fused_step() + scalars.cpu()"}
+
+    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_port(N, B, args.cpu_steps, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{r['cycles']} cycle(s) x {r['m']} train steps x batch {B} at N=2^{args.log2n} priorities "
+                         f"(pool of 2048 pickled records), {r['seconds']:.1f} s of CPU work",
+               "parts_s_per_cycle": r["parts"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "clocks": clock_info,
+                "cuda_graph": use_graph, "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

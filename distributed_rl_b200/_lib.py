@@ -29,10 +29,12 @@ SIGNATURES = {
     "b2rl_replay_evict": (C.c_int, [c_vp, c_i64, c_vp]),
     "b2rl_replay_fill_hash": (C.c_int, [c_vp, c_i64, c_u32, c_vp]),
     "b2rl_tree_build": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
-    "b2rl_tree_sample": (C.c_int, [c_vp, c_vp, c_u64, c_u64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "b2rl_tree_sample": (C.c_int, [c_vp, c_vp, c_u64, c_u64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2rl_replay_seed": (C.c_int, [c_vp, c_u64, c_u64, c_vp]),
+    "b2rl_tree_sample_stream": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2rl_philox_uniforms": (C.c_int, [c_u64, c_u64, c_i64, c_vp, c_vp]),
     "b2rl_tree_update": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "b2rl_tree_stats": (C.c_int, [c_vp, c_f32, c_vp, c_vp]),
+    "b2rl_tree_stats": (C.c_int, [c_vp, c_f32, c_vp, c_vp, c_vp]),
     "b2rl_tree_leaves": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "b2rl_replay_gather": (C.c_int, [c_vp, c_vp, c_i64, C.POINTER(c_vp), c_vp]),
     "b2rl_apex_target": (C.c_int, [c_vp] * 7 + [c_i32, c_i32, c_f32, c_f32] + [c_vp] * 6),

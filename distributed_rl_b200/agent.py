@@ -1,0 +1,207 @@
+"""GraphAgent — the Q / policy network the targets are computed from.
+
+The reference describes its networks as a JSON graph of named nodes executed in
+`prior` order (baseline/baseAgent.py:60-180, 287-309; layer zoo in
+baseline/baseNetwork.py).  The network is a *callee* of the hot path and stays
+plain PyTorch; this module is an independent,
+much smaller interpreter for the node types the three shipped configs use
+(cfg/ape_x.json, cfg/r2d2.json, cfg/impala.json):
+
+    CNN2D  MLP  LSTMNET  ViewV2  Add  Mean  Substract
+
+with the same call surface the learners rely on: forward([inputs]) -> tuple,
+getParameters, updateParameter(other, tau), setCellState / detachCellState /
+zeroCellState, calculateNorm, clippingNorm, and state_dict() key names
+(`module00.conv_1.weight`, `module02.MLP_1.weight`, `module02.rnn.weight_ih_l0`,
+...) so that reference actors can load the weights this learner publishes.
+All layers are bias-free, as in the reference (baseNetwork.py:77-79,165-172).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+_ACT = {"relu": nn.ReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid, "linear": None}
+
+
+def _act(name):
+    if name not in _ACT:
+        raise ValueError(f"unsupported activation {name!r}")
+    return None if _ACT[name] is None else _ACT[name]()
+
+
+class ConvStack(nn.Sequential):
+    """netCat CNN2D: conv layers (bias=False), then Flatten at fSize == -1."""
+
+    def __init__(self, d):
+        super().__init__()
+        ch = d["iSize"]
+        acts = list(d["act"]) if isinstance(d["act"], list) else [d["act"]] * d["nLayer"]
+        for i, k in enumerate(d["fSize"]):
+            if k == -1:
+                self.add_module("Flatten", nn.Flatten())
+                continue
+            self.add_module(f"conv_{i + 1}", nn.Conv2d(ch, d["nUnit"][i], k, stride=d["stride"][i],
+                                                       padding=d["padding"][i], bias=False))
+            ch = d["nUnit"][i]
+            a = _act(acts[i]) if i < len(acts) else None
+            if a is not None:
+                self.add_module(f"act_{i + 1}", a)
+
+    def forward(self, xs):
+        x = xs[0] if isinstance(xs, (tuple, list)) else xs
+        for layer in self:
+            x = layer(x)
+        return x
+
+
+class DenseStack(nn.Sequential):
+    """netCat MLP: Linear layers (bias off unless cfg says so) with activations."""
+
+    def __init__(self, d):
+        super().__init__()
+        n_in = d["iSize"]
+        acts = d["act"] if isinstance(d["act"], list) else [d["act"]] * d["nLayer"]
+        bias = bool(d.get("bias", False))
+        for i in range(d["nLayer"]):
+            self.add_module(f"MLP_{i + 1}", nn.Linear(n_in, d["fSize"][i], bias=bias))
+            n_in = d["fSize"][i]
+            a = _act(acts[i])
+            if a is not None:
+                self.add_module(f"act_{i + 1}", a)
+
+    def forward(self, xs):
+        x = xs[0] if isinstance(xs, (tuple, list)) else xs
+        for layer in self:
+            x = layer(x)
+        return x
+
+
+class Recurrent(nn.Module):
+    """netCat LSTMNET: single-layer LSTM that carries its cell state between calls."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.hidden = d["hiddenSize"]
+        self.flatten = bool(d.get("FlattenMode", False))
+        self.return_hidden = bool(d.get("return_hidden", False))
+        self.rnn = nn.LSTM(d["iSize"], self.hidden, d.get("nLayer", 1))
+        self.state = None
+
+    def set_state(self, hc):
+        self.state = hc
+
+    def detach_state(self):
+        if self.state is not None:
+            self.state = (self.state[0].detach().clone(), self.state[1].detach().clone())
+
+    def zero_state(self, num=1):
+        p = next(self.rnn.parameters())
+        z = torch.zeros(1, num, self.hidden, device=p.device, dtype=p.dtype)
+        self.state = (z, z.clone())
+
+    def forward(self, xs):
+        x = xs[0]
+        if self.state is None:
+            self.zero_state(x.shape[1])
+        out, hc = self.rnn(x, self.state)
+        self.state = hc
+        if self.return_hidden:
+            return out[-1:]
+        if self.flatten:
+            out = out.reshape(-1, self.hidden)
+        return out
+
+
+class ViewAs(nn.Module):
+    """netCat ViewV2: inputs = (shape tensor, activations) -> activations.view(shape)."""
+
+    def forward(self, xs):
+        shape, x = xs[0], xs[1]
+        dims = tuple(int(v) for v in (shape.tolist() if torch.is_tensor(shape) else shape))
+        return x.view(dims)
+
+
+class _Add(nn.Module):
+    def forward(self, xs):
+        return xs[0] + xs[1]
+
+
+class _Sub(nn.Module):
+    def forward(self, xs):
+        return xs[0] - xs[1]
+
+
+class _Mean(nn.Module):
+    def forward(self, xs):
+        return xs[0].mean(dim=-1, keepdim=True)
+
+
+_NODE = {"CNN2D": ConvStack, "MLP": DenseStack, "LSTMNET": Recurrent,
+         "ViewV2": lambda d: ViewAs(), "Add": lambda d: _Add(), "Substract": lambda d: _Sub(),
+         "Mean": lambda d: _Mean()}
+
+
+class GraphAgent(nn.Module):
+    def __init__(self, model_cfg: dict):
+        super().__init__()
+        self.cfg = model_cfg
+        order = sorted(model_cfg, key=lambda n: (model_cfg[n]["prior"], n))
+        self._order = order
+        self._ext = {}      # node -> list of external input ids
+        self._prev = {}     # node -> list of upstream node names
+        self._outputs = [n for n in sorted(model_cfg) if model_cfg[n].get("output")]
+        self._recurrent = []
+        for name in order:
+            d = model_cfg[name]
+            kind = d["netCat"]
+            if kind not in _NODE:
+                raise ValueError(f"node type {kind!r} is not used by the shipped configs and is not supported")
+            setattr(self, name, _NODE[kind](d))
+            self._ext[name] = list(d.get("input", []))
+            self._prev[name] = list(d.get("prevNodeNames", []))
+            if kind == "LSTMNET":
+                self._recurrent.append(name)
+
+    # -- execution: external inputs first, then upstream outputs (reference order) --
+    def forward(self, inputs):
+        vals = {}
+        for name in self._order:
+            srcs = [inputs[i] for i in self._ext[name]] + [vals[p] for p in self._prev[name]]
+            vals[name] = getattr(self, name)(tuple(srcs))
+        return tuple(vals[n] for n in self._outputs)
+
+    # -- the surface the learners call --------------------------------------------
+    def getParameters(self):
+        return list(self.parameters())
+
+    def updateParameter(self, other: "GraphAgent", tau: float) -> None:
+        with torch.no_grad():
+            mine, theirs = list(self.parameters()), list(other.parameters())
+            if tau == 1:
+                torch._foreach_copy_(mine, theirs)
+            else:
+                torch._foreach_mul_(mine, 1 - tau)
+                torch._foreach_add_(mine, theirs, alpha=tau)
+
+    def calculateNorm(self):
+        return sum(p.grad.norm(2) for p in self.parameters() if p.grad is not None)
+
+    def clippingNorm(self, max_norm):
+        torch.nn.utils.clip_grad_norm_(list(self.parameters()), max_norm)
+
+    def _rec(self, name=None) -> Recurrent:
+        return getattr(self, name or self._recurrent[0])
+
+    def setCellState(self, hc, name=None):
+        self._rec(name).set_state(hc)
+
+    def getCellState(self, name=None):
+        h, c = self._rec(name).state
+        return h.clone(), c.clone()
+
+    def detachCellState(self, name=None):
+        self._rec(name).detach_state()
+
+    def zeroCellState(self, num=1, name=None):
+        self._rec(name).zero_state(num)

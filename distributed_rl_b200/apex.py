@@ -1,0 +1,375 @@
+"""Ape-X learner side: `Replay` and `Learner` with the reference's surface
+(APE_X/ReplayMemory.py:19-167, APE_X/Learner.py:20-272) on top of the
+HBM-resident replay and the fused kernels.
+
+What changed relative to the reference, and why it is still a drop-in:
+  * replay contents + priorities live in HBM (DeviceReplay); `Replay.sample()`
+    returns the same 7-list `[s, a, r, s', done, w, idx]`, but as CUDA tensors,
+    so `Learner.train` never copies frames host->device (the reference converts
+    to fp32 on the CPU and ships 4x the bytes, APE_X/Learner.py:61-67).
+  * `Learner.train` has no device->host sync: double-DQN argmax, target, clipped
+    TD, priority, loss and dLoss/dQ come from one kernel (b2rl_apex_target) and
+    the network backward is seeded with dLoss/dQ directly.
+  * priorities are written back immediately (`Replay.update` enqueues the tree
+    update on the stream) instead of after >1000 pending entries
+    (APE_X/ReplayMemory.py:147-150); eviction is the ring's FIFO overwrite, so
+    the `lock` flag handshake (:151-160, APE_X/Learner.py:189-197) is a no-op.
+  * `Learner.fused_step()` runs sample -> gather -> 3 forwards -> target ->
+    backward -> RMSprop -> priority write-back as one CUDA graph.
+"""
+from __future__ import annotations
+
+import pickle
+import threading
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import replay as R
+from .agent import GraphAgent
+
+
+@dataclass
+class ApexConfig:
+    """The globals the reference lifts out of cfg/ape_x.json (configuration.py:39-98)."""
+    BATCHSIZE: int = 32
+    ACTION_SIZE: int = 6
+    ALPHA: float = 0.6
+    BETA: float = 0.4
+    GAMMA: float = 0.99
+    UNROLL_STEP: int = 3
+    REPLAY_MEMORY_LEN: int = 100000
+    BUFFER_SIZE: int = 50000
+    TARGET_FREQUENCY: int = 2500
+    LEARNER_DEVICE: str = "cuda:0"
+    REDIS_SERVER: str = "localhost"
+    OPTIM_INFO: dict = field(default_factory=lambda: {
+        "name": "rmsprop", "lr": 0.0000625, "eps": 1.5e-7, "decay": 0, "alpha": 0.95, "momentum": 0,
+        "centered": True})
+    MODEL: dict = field(default_factory=lambda: default_apex_model())
+
+    @staticmethod
+    def from_configuration():
+        import configuration as C  # the drop-in module (dropin/configuration.py) or the user's own
+        kw = {k: getattr(C, k) for k in ("BATCHSIZE", "ACTION_SIZE", "ALPHA", "BETA", "GAMMA", "UNROLL_STEP",
+                                         "REPLAY_MEMORY_LEN", "BUFFER_SIZE", "TARGET_FREQUENCY",
+                                         "LEARNER_DEVICE", "REDIS_SERVER", "OPTIM_INFO", "MODEL")}
+        return ApexConfig(**kw)
+
+
+def default_apex_model() -> dict:
+    """The dueling DQN of cfg/ape_x.json:37-88 (values are configuration, not code)."""
+    return {
+        "module00": {"netCat": "CNN2D", "iSize": 4, "nLayer": 4, "fSize": [8, 4, 3, -1], "nUnit": [32, 64, 64],
+                     "padding": [0, 0, 0], "stride": [4, 2, 1], "act": ["relu", "relu", "relu"],
+                     "BN": [False] * 4, "linear": True, "input": [0], "prior": 0},
+        "module02": {"netCat": "MLP", "iSize": 3136, "nLayer": 2, "fSize": [512, 6], "act": ["relu", "linear"],
+                     "BN": [False] * 3, "prior": 1, "prevNodeNames": ["module00"]},
+        "module02_1": {"netCat": "MLP", "iSize": 3136, "nLayer": 2, "fSize": [512, 1], "act": ["relu", "linear"],
+                       "BN": [False] * 3, "prior": 1, "prevNodeNames": ["module00"]},
+        "module03": {"netCat": "Add", "prior": 2, "prevNodeNames": ["module02", "module02_1"]},
+        "module03_1": {"netCat": "Mean", "prior": 2, "prevNodeNames": ["module02"]},
+        "module04": {"netCat": "Substract", "prior": 3, "prevNodeNames": ["module03", "module03_1"],
+                     "output": True},
+    }
+
+
+def make_optimizer(info: dict, params, capturable: bool = True):
+    """baseline/utils.py getOptim (:78-132) for the optimisers the shipped configs name."""
+    name = info["name"]
+    lr, decay, eps = info["lr"], info.get("decay", 0), info.get("eps", 1e-5)
+    if name == "rmsprop":
+        return torch.optim.RMSprop(params, lr=lr, weight_decay=decay, eps=eps, momentum=info.get("momentum", 0),
+                                   alpha=info.get("alpha", 0.99), centered=info.get("centered", False),
+                                   capturable=capturable, foreach=True)
+    if name == "adam":
+        return torch.optim.Adam(params, lr=lr, weight_decay=decay, eps=eps,
+                                betas=(info.get("beta1", 0.9), info.get("beta2", 0.99)),
+                                capturable=capturable, foreach=True)
+    if name == "sgd":
+        return torch.optim.SGD(params, lr=lr, weight_decay=decay, momentum=info.get("momentum", 0))
+    raise ValueError(f"unknown optimizer {name!r}")
+
+
+class _MemoryView:
+    """What the learner reads from `Replay.memory` (APE_X/Learner.py:143,241):
+    len() and .max_weight (baseline/PER.py:80-81,129-133)."""
+
+    def __init__(self, dev_replay: R.DeviceReplay, beta: float):
+        self._r, self._beta = dev_replay, beta
+
+    def __len__(self):
+        return len(self._r)
+
+    @property
+    def max_weight(self) -> float:
+        return float(self._r.stats(self._beta)[2].item())
+
+
+class Replay(threading.Thread):
+    """APE_X/ReplayMemory.py Replay (:19-167): same methods and attributes."""
+
+    def __init__(self, cfg: ApexConfig | None = None, connect=None):
+        super().__init__(daemon=True)
+        self.cfg = cfg or ApexConfig.from_configuration()
+        self.device = torch.device(self.cfg.LEARNER_DEVICE)
+        self.store = R.DeviceReplay(self.cfg.REPLAY_MEMORY_LEN, R.APEX_FIELDS, self.device)
+        self.memory = _MemoryView(self.store, self.cfg.BETA)
+        self.connect = connect
+        self.cond = False
+        self.lock = False          # eviction handshake flag: kept for API compatibility, unused
+        self.deque = []            # pre-assembled minibatches (filled on demand)
+        self.total_frame = 0
+        self._lock = threading.Lock()
+        self._stop = False
+
+    # -- ingest: records are [s, a, R_n, s', done, prio] pickled by the actors ----
+    def push_records(self, blobs) -> None:
+        """PER.push (baseline/PER.py:69-75) for a list of pickled actor records
+        (APE_X/Player.py:252-261): decoded once on the host, then one batched
+        H2D copy + fused leaf write / path refresh."""
+        if not blobs:
+            return
+        recs = [pickle.loads(b) for b in blobs]
+        n = len(recs)
+        s = np.stack([np.asarray(r[0], np.uint8) for r in recs])
+        ns = np.stack([np.asarray(r[3], np.uint8) for r in recs])
+        a = np.asarray([int(r[1]) for r in recs], np.int32)
+        rw = np.asarray([float(r[2]) for r in recs], np.float32)
+        d = np.asarray([bool(r[4]) for r in recs], np.uint8)
+        p = np.asarray([float(r[5]) for r in recs], np.float32)
+        with self._lock:
+            self.store.push([s, ns, a, rw, d], p)
+        self.total_frame += n
+
+    def push_arrays(self, s, ns, a, r, d, p) -> None:
+        """Same ingest for already-decoded arrays (host pinned or device)."""
+        with self._lock:
+            self.store.push([s, ns, a, r, d], p)
+        self.total_frame += int(torch.as_tensor(p).numel())
+
+    def run(self):
+        """Poll the actors' Redis list like APE_X/ReplayMemory.py:118-161."""
+        if self.connect is None:
+            return
+        while not self._stop:
+            pipe = self.connect.pipeline()
+            pipe.lrange("experience", 0, -1)
+            pipe.ltrim("experience", -1, 0)
+            data = pipe.execute()[0]
+            if data:
+                self.push_records(data)
+                self.cond = len(self.store) > 50000
+            else:
+                time.sleep(0.002)
+
+    # -- sampling -------------------------------------------------------------------
+    def buffer(self, m: int = 1) -> None:
+        """Replay.buffer (:61-116): sample m*BATCHSIZE, IS weights, assemble minibatches."""
+        B = self.cfg.BATCHSIZE
+        with self._lock:
+            idx, _, w = self.store.sample(B * m, beta=self.cfg.BETA)
+            batch = self.store.gather(idx)
+        for k in range(m):
+            sl = slice(k * B, (k + 1) * B)
+            self.deque.append([batch["state"][sl], batch["action"][sl], batch["reward"][sl],
+                               batch["next_state"][sl], batch["done"][sl], w[sl], idx[sl]])
+
+    def sample(self):
+        if len(self.deque) == 0:
+            if len(self.store) <= self.cfg.BUFFER_SIZE:
+                return False
+            self.buffer(1)
+        return self.deque.pop(0)
+
+    # -- priority write-back ----------------------------------------------------------
+    def update(self, idx, vals) -> None:
+        """Replay.update (:43-47) + _update (:49-59) -> PER.update: applied at once."""
+        if isinstance(idx, (list, tuple)):
+            idx = torch.stack([torch.as_tensor(i) for i in idx]) if len(idx) and torch.is_tensor(idx[0]) \
+                else torch.as_tensor(np.asarray(idx, np.int64))
+        vals = torch.as_tensor(vals)
+        with self._lock:
+            self.store.update(idx.to(self.device), vals.to(self.device))
+
+    def _update(self):
+        return None
+
+
+class Learner:
+    """APE_X/Learner.py Learner (:20-272): train / step / run / state_dict."""
+
+    def __init__(self, cfg: ApexConfig | None = None, connect=None, start_replay: bool = True,
+                 writer=None):
+        self.cfg = cfg or ApexConfig.from_configuration()
+        self.device = torch.device(self.cfg.LEARNER_DEVICE)
+        self.build_model()
+        self.build_optim()
+        self.connect = connect
+        self.memory = Replay(self.cfg, connect)
+        if start_replay and connect is not None:
+            self.memory.start()
+        self.writer = writer
+        self.gamma_n = float(np.float32(0.99 ** self.cfg.UNROLL_STEP))  # hard-coded 0.99, :103
+        self._graph = None
+        self._world = 1
+        self.launches_per_step = None   # libb2rl kernels per fused step (bench.py's gpu_launches)
+
+    def enable_data_parallel(self):
+        """Replay-sharded data parallelism: every rank owns a replay shard and
+        samples locally; per step one NCCL all-reduce (AVG) of the gradients, kept in ONE flat
+        bucket so it is a single collective, and one MAX all-reduce of the max IS weight."""
+        import torch.distributed as dist
+        self._dist = dist
+        self._world = dist.get_world_size()
+        params = self.model.getParameters()
+        self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=self.device)
+        off = 0
+        for p in params:
+            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)
+
+    def build_model(self):
+        self.model = GraphAgent(self.cfg.MODEL).to(self.device)
+        self.target_model = GraphAgent(self.cfg.MODEL).to(self.device)
+
+    def build_optim(self):
+        self.optim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
+
+    # -- one training step on an explicit minibatch (reference signature) -----------
+    def _to_dev(self, x, dtype):
+        if torch.is_tensor(x):
+            return x.to(device=self.device, dtype=dtype, non_blocking=True)
+        if isinstance(x, np.ndarray) and x.dtype == object:
+            x = x.astype(np.float64 if dtype.is_floating_point else np.int64)
+        return torch.as_tensor(x).to(device=self.device, dtype=dtype, non_blocking=True)
+
+    def _forward_backward(self, state, action, reward, next_state, done, weight):
+        s = state.to(torch.float32) / 255.0            # :61-63 (on the device: no fp32 H2D)
+        ns = next_state.to(torch.float32) / 255.0      # :65-67
+        q = self.model.forward([s])[0]                 # :78
+        with torch.no_grad():
+            qn_target = self.target_model.forward([ns])[0]   # :85
+            qn_online = self.model.forward([ns])[0]          # :87
+        notdone = 1.0 - done.to(torch.float32)         # :76
+        out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
+                            self.gamma_n, self.cfg.ALPHA)
+        q.backward(out["grad_q"])                      # == loss.backward(), :112-115
+        if self._world > 1:
+            self._dist.all_reduce(self._flat_grad, op=self._dist.ReduceOp.AVG)
+        return out
+
+    def train(self, transition, t=0):
+        state, action, reward, next_state, done, weight, idx = transition
+        state = self._to_dev(state, torch.uint8)
+        next_state = self._to_dev(next_state, torch.uint8)
+        action = self._to_dev(action, torch.int64)
+        reward = self._to_dev(reward, torch.float32)
+        done = self._to_dev(done, torch.uint8) if not (torch.is_tensor(done) and done.dtype == torch.bool) \
+            else done.to(self.device, torch.uint8)
+        weight = self._to_dev(weight, torch.float32)
+        out = self._forward_backward(state, action, reward, next_state, done, weight)
+        info = self.step()
+        info["mean_value"] = out["scalars"][1]
+        info["loss"] = out["scalars"][0]
+        return info, out["prio"], idx, out["scalars"][2]
+
+    def step(self):
+        """Learner.step (:123-138): 'norm' = sqrt(sum_i ||g_i||_2) (sic), RMSprop, zero_grad."""
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        p_norm = torch.stack(torch._foreach_norm(grads, 2)).sum().sqrt()
+        self.optim.step()
+        self.optim.zero_grad(set_to_none=False)
+        return {"p_norm": p_norm}
+
+    # -- the whole hot loop iteration as one CUDA graph -----------------------------------
+    def fused_step(self, use_graph: bool = True):
+        """sample -> gather -> forwards -> target -> backward -> RMSprop -> priority
+        write-back (APE_X/Learner.py:165-197) with no host round trip."""
+        if self._graph is not None:
+            self._graph.replay()
+            return self._static
+        B = self.cfg.BATCHSIZE
+        st = self.memory.store
+
+        def body():
+            max_w = None
+            if self._world > 1:      # priority-max reduction: normalise IS weights by the global max
+                max_w = st.max_weight(self.cfg.BETA, out=self._max_w)
+                self._dist.all_reduce(max_w, op=self._dist.ReduceOp.MAX)
+            idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
+            b = st.gather(idx)
+            out = self._forward_backward(b["state"], b["action"].to(torch.int64), b["reward"],
+                                         b["next_state"], b["done"], w)
+            info = self.step()
+            st.update(idx, out["prio"])
+            return {"scalars": out["scalars"], "p_norm": info["p_norm"], "prio": out["prio"], "idx": idx}
+
+        lib = st.lib
+        if not use_graph:
+            c0 = lib.b2rl_launch_count()
+            r = body()
+            self.launches_per_step = lib.b2rl_launch_count() - c0
+            return r
+        self.optim.zero_grad(set_to_none=False)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):   # warm-up: lazy inits (cuDNN plans, optimizer state) happen outside capture
+                body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        c0 = lib.b2rl_launch_count()
+        with torch.cuda.graph(g):
+            self._static = body()
+        self.launches_per_step = lib.b2rl_launch_count() - c0   # recorded into the graph, replayed each step
+        self._graph = g
+        g.replay()
+        return self._static
+
+    # -- parameter publication / main loop -------------------------------------------------
+    @property
+    def state_dict(self):
+        return {k: v.cpu() for k, v in self.model.state_dict().items()}
+
+    @property
+    def target_state_dict(self):
+        return {k: v.cpu() for k, v in self.target_model.state_dict().items()}
+
+    def run(self, max_steps: int | None = None, log_every: int = 500):
+        """Learner.run (:140-262) — same cadence of target sync (TARGET_FREQUENCY) and
+        parameter publication (every 50 steps) when a Redis connection is present."""
+        while len(self.memory.memory) <= self.cfg.BUFFER_SIZE:
+            time.sleep(0.05)
+        if self.connect is not None:
+            self.connect.set("state_dict", pickle.dumps(self.state_dict))
+            self.connect.set("count", pickle.dumps(1))
+            self.connect.set("target_state_dict", pickle.dumps(self.target_state_dict))
+            self.connect.set("Start", pickle.dumps(True))
+        step = 0
+        t0 = time.time()
+        acc = None
+        while max_steps is None or step < max_steps:
+            out = self.fused_step()
+            step += 1
+            acc = out["scalars"].clone() if acc is None else acc + out["scalars"]
+            if step % self.cfg.TARGET_FREQUENCY == 0:
+                self.target_model.updateParameter(self.model, 1)
+                if self.connect is not None:
+                    self.connect.set("target_state_dict", pickle.dumps(self.target_state_dict))
+            if step % 50 == 0 and self.connect is not None:
+                self.connect.set("state_dict", pickle.dumps(self.state_dict))
+                self.connect.set("count", pickle.dumps(step - 50))
+            if step % log_every == 0:
+                loss, mean_value, mean_w = (acc / log_every).tolist()
+                dt = (time.time() - t0) / log_every
+                print(f"step:{step} // mean_value:{mean_value:.3f} // loss:{loss:.5f} // NUM_MEMORY:"
+                      f"{len(self.memory.memory)} // Mean_Weight:{mean_w:.3f} // TIME:{dt:.5f}")
+                if self.writer is not None:
+                    self.writer.add_scalar("value", mean_value, step)
+                acc, t0 = None, time.time()
+        return step

@@ -32,6 +32,7 @@ static void free_all(b2rl_replay* h) {
   if (h->tag) cudaFree(h->tag);
   if (h->mark) cudaFree(h->mark);
   if (h->scratch_val) cudaFree(h->scratch_val);
+  if (h->rng_dev) cudaFree(h->rng_dev);
 }
 
 extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) {
@@ -65,6 +66,7 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
   alloc((void**)&h->tag, sizeof(uint32_t) * (size_t)h->cap2);
   alloc((void**)&h->mark, sizeof(int32_t) * (size_t)h->cap2);
   alloc((void**)&h->scratch_val, sizeof(float) * (size_t)h->capacity);
+  alloc((void**)&h->rng_dev, sizeof(uint64_t) * 2);
   if (e != cudaSuccess) {
     set_error("cudaMalloc failed while creating a %lld-slot replay: %s", (long long)d->capacity,
               cudaGetErrorString(e));
@@ -78,6 +80,10 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
   B2RL_CUDA(cudaMemset(h->minv, 0x7f, sizeof(float) * 2 * (size_t)h->cap2));  // 0x7f7f7f7f ~ 3.4e38
   B2RL_CUDA(cudaMemset(h->tag, 0, sizeof(uint32_t) * (size_t)h->cap2));
   B2RL_CUDA(cudaMemset(h->mark, 0, sizeof(int32_t) * (size_t)h->cap2));
+  {
+    const uint64_t init[2] = {1234ULL, 0ULL};
+    B2RL_CUDA(cudaMemcpy(h->rng_dev, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
   B2RL_CUDA(cudaDeviceSynchronize());
   *out = h;
   return B2RL_OK;

@@ -111,6 +111,7 @@ struct b2rl_replay {
   int32_t* mark = nullptr;    // [cap2]   per-internal-node side bits + arrival count, self-cleaning
   int64_t* scratch_idx = nullptr;  // [capacity] ring indices for push/evict
   float* scratch_val = nullptr;    // [capacity]
+  uint64_t* rng_dev = nullptr;     // [2] device-resident Philox stream {seed, counter}
   int64_t size = 0;       // valid slots
   int64_t head = 0;       // next slot to write
 };

@@ -90,11 +90,13 @@ constexpr int SAMPLE_THREADS = 128;
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 k_tree_sample(const double* __restrict__ sum, const float* __restrict__ minv, int64_t cap2,
               int levels, const double* __restrict__ u01, uint64_t seed, uint64_t rng_offset,
-              int64_t n, float n_valid, float beta, int64_t* __restrict__ idx_out,
+              const uint64_t* __restrict__ rng_state, int64_t n, float n_valid, float beta,
+              const float* __restrict__ max_w_ext, int64_t* __restrict__ idx_out,
               float* __restrict__ prob_out, float* __restrict__ w_out) {
   const int64_t k = (int64_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x;
   if (k >= n) return;
   const double root = sum[1];
+  if (rng_state) { seed = rng_state[0]; rng_offset = rng_state[1]; }
   const double u = u01 ? u01[k] : philox_u01(seed, rng_offset + (uint64_t)k);
   double pos = __dmul_rn(root, u);  // np.random.uniform(0, root) == root * random_sample()
   int64_t i = 1;
@@ -116,10 +118,20 @@ k_tree_sample(const double* __restrict__ sum, const float* __restrict__ minv, in
   if (prob_out) prob_out[k] = prob;
   if (w_out) {
     const float w_un = powcr(__fdiv_rn(1.0f, __fmul_rn(n_valid, prob)), beta);
-    const float min_prob = __fdiv_rn(minv[1], s32);
-    const float max_w = powcr(__fmul_rn(n_valid, min_prob), -beta);
+    float max_w;
+    if (max_w_ext) {
+      max_w = *max_w_ext;
+    } else {
+      const float min_prob = __fdiv_rn(minv[1], s32);
+      max_w = powcr(__fmul_rn(n_valid, min_prob), -beta);
+    }
     w_out[k] = __fdiv_rn(w_un, max_w);
   }
+}
+
+__global__ void k_rng_advance(uint64_t* __restrict__ rng_state, uint64_t n) { rng_state[1] += n; }
+__global__ void k_rng_seed(uint64_t* __restrict__ rng_state, uint64_t seed, uint64_t ctr) {
+  rng_state[0] = seed; rng_state[1] = ctr;
 }
 
 __global__ void k_philox_uniforms(uint64_t seed, uint64_t off, int64_t n, double* __restrict__ out) {
@@ -128,13 +140,14 @@ __global__ void k_philox_uniforms(uint64_t seed, uint64_t off, int64_t n, double
 }
 
 __global__ void k_tree_stats(const double* __restrict__ sum, const float* __restrict__ minv,
-                             float n_valid, float beta, double* __restrict__ out) {
+                             float n_valid, float beta, double* __restrict__ out,
+                             float* __restrict__ max_w_out) {
   const double root = sum[1];
   const float s32 = (float)root;
   const float mn = minv[1];
-  out[0] = root;
-  out[1] = (double)mn;
-  out[2] = (double)powcr(__fmul_rn(n_valid, __fdiv_rn(mn, s32)), -beta);
+  const float mw = powcr(__fmul_rn(n_valid, __fdiv_rn(mn, s32)), -beta);
+  if (out) { out[0] = root; out[1] = (double)mn; out[2] = (double)mw; }
+  if (max_w_out) *max_w_out = mw;
 }
 
 __global__ void k_tree_leaves(const double* __restrict__ sum, int64_t cap2, int64_t start, int64_t n,
@@ -263,8 +276,9 @@ extern "C" int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n
 }
 
 extern "C" int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t seed,
-                                uint64_t rng_offset, int64_t n, float beta, int64_t* idx_out_dev,
-                                float* prob_out_dev, float* w_out_dev, void* stream) {
+                                uint64_t rng_offset, int64_t n, float beta, const float* max_w_dev,
+                                int64_t* idx_out_dev, float* prob_out_dev, float* w_out_dev,
+                                void* stream) {
   B2RL_REQUIRE(h != nullptr, "null handle");
   B2RL_REQUIRE(n >= 0, "negative n");
   B2RL_REQUIRE(h->size > 0, "sampling from an empty replay");
@@ -272,9 +286,37 @@ extern "C" int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t 
   if (n == 0) return B2RL_OK;
   DeviceGuard g(h->device);
   k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(
-      h->sum, h->minv, h->cap2, h->levels, u01_dev, seed, rng_offset, n, (float)h->size, beta,
-      idx_out_dev, prob_out_dev, w_out_dev);
+      h->sum, h->minv, h->cap2, h->levels, u01_dev, seed, rng_offset, nullptr, n, (float)h->size, beta,
+      max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
   count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_seed(b2rl_replay* h, uint64_t seed, uint64_t counter, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  DeviceGuard g(h->device);
+  k_rng_seed<<<1, 1, 0, (cudaStream_t)stream>>>(h->rng_dev, seed, counter);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_tree_sample_stream(b2rl_replay* h, int64_t n, float beta, const float* max_w_dev,
+                                       int64_t* idx_out_dev, float* prob_out_dev, float* w_out_dev,
+                                       void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 0, "negative n");
+  B2RL_REQUIRE(h->size > 0, "sampling from an empty replay");
+  B2RL_REQUIRE(n == 0 || idx_out_dev != nullptr, "null idx_out");
+  if (n == 0) return B2RL_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, st>>>(
+      h->sum, h->minv, h->cap2, h->levels, nullptr, 0, 0, h->rng_dev, n, (float)h->size, beta,
+      max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
+  k_rng_advance<<<1, 1, 0, st>>>(h->rng_dev, (uint64_t)n);
+  count_launch(2);
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
 }
@@ -299,10 +341,12 @@ extern "C" int b2rl_tree_update(b2rl_replay* h, const int64_t* idx_dev, const fl
   return b2rl_tree_update_impl(h, idx_dev, 0, vals_dev, 0.0f, n, (cudaStream_t)stream);
 }
 
-extern "C" int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev, void* stream) {
-  B2RL_REQUIRE(h != nullptr && stats_out_dev != nullptr, "null argument");
+extern "C" int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev, float* max_w_out_dev,
+                               void* stream) {
+  B2RL_REQUIRE(h != nullptr && (stats_out_dev != nullptr || max_w_out_dev != nullptr), "null argument");
   DeviceGuard g(h->device);
-  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->sum, h->minv, (float)h->size, beta, stats_out_dev);
+  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->sum, h->minv, (float)h->size, beta, stats_out_dev,
+                                                  max_w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;

@@ -108,8 +108,6 @@ class DeviceReplay:
         h = C.c_void_p()
         check(self.lib.b2rl_replay_create(C.byref(d), C.byref(h)))
         self._h = h
-        self._rng_offset = 0
-        self.seed = 1234
 
     # -- bookkeeping -----------------------------------------------------------
     def close(self):
@@ -190,26 +188,40 @@ class DeviceReplay:
         p = priorities.to(device=self.device, dtype=torch.float32).contiguous()
         check(self.lib.b2rl_tree_build(self._h, p.data_ptr(), p.numel(), self._st()))
 
+    def seed(self, seed: int, counter: int = 0) -> None:
+        """(Re)seed the device-resident Philox stream used when no uniforms are passed."""
+        check(self.lib.b2rl_replay_seed(self._h, int(seed), int(counter), self._st()))
+
     def sample(self, n: int, beta: float = 0.4, u01: torch.Tensor | None = None,
-               want_prob: bool = True, out=None):
-        """-> (idx int64[n], prob fp32[n], weight fp32[n]) on the device."""
+               want_prob: bool = True, out=None, max_w: torch.Tensor | None = None):
+        """-> (idx int64[n], prob fp32[n], weight fp32[n]) on the device.
+        With explicit fp64 uniforms `u01` (parity runs) or, if None, from the
+        handle's device-resident Philox stream (graph-replayable)."""
         if out is None:
             idx = torch.empty(n, dtype=torch.int64, device=self.device)
             prob = torch.empty(n, dtype=torch.float32, device=self.device) if want_prob else None
             w = torch.empty(n, dtype=torch.float32, device=self.device)
         else:
             idx, prob, w = out
+        pp = prob.data_ptr() if prob is not None else None
+        mw = max_w.data_ptr() if max_w is not None else None   # all-reduced max IS weight (multi-GPU)
         if u01 is not None:
             u01 = u01.to(device=self.device, dtype=torch.float64).contiguous()
             assert u01.numel() == n
-            up = u01.data_ptr()
+            check(self.lib.b2rl_tree_sample(self._h, u01.data_ptr(), 0, 0, n, float(beta), mw,
+                                            idx.data_ptr(), pp, w.data_ptr(), self._st()))
         else:
-            up = None
-        check(self.lib.b2rl_tree_sample(self._h, up, self.seed, self._rng_offset, n, float(beta),
-                                        idx.data_ptr(), prob.data_ptr() if prob is not None else None,
-                                        w.data_ptr(), self._st()))
-        if u01 is None:
-            self._rng_offset += n
+            check(self.lib.b2rl_tree_sample_stream(self._h, n, float(beta), mw, idx.data_ptr(), pp,
+                                                   w.data_ptr(), self._st()))
+        return idx, prob, w
+
+    def sample_counter(self, seed: int, counter: int, n: int, beta: float = 0.4):
+        """Stateless Philox draw: uniform k = philox(seed, counter + k)."""
+        idx = torch.empty(n, dtype=torch.int64, device=self.device)
+        prob = torch.empty(n, dtype=torch.float32, device=self.device)
+        w = torch.empty(n, dtype=torch.float32, device=self.device)
+        check(self.lib.b2rl_tree_sample(self._h, None, int(seed), int(counter), n, float(beta), None,
+                                        idx.data_ptr(), prob.data_ptr(), w.data_ptr(), self._st()))
         return idx, prob, w
 
     def philox_uniforms(self, seed: int, offset: int, n: int) -> torch.Tensor:
@@ -226,7 +238,13 @@ class DeviceReplay:
     def stats(self, beta: float = 0.4) -> torch.Tensor:
         """device tensor fp64[3] = {sum(p), min p, max IS weight}."""
         out = torch.empty(3, dtype=torch.float64, device=self.device)
-        check(self.lib.b2rl_tree_stats(self._h, float(beta), out.data_ptr(), self._st()))
+        check(self.lib.b2rl_tree_stats(self._h, float(beta), out.data_ptr(), None, self._st()))
+        return out
+
+    def max_weight(self, beta: float = 0.4, out: torch.Tensor | None = None) -> torch.Tensor:
+        """device fp32[1]: this shard's max IS weight (operand of the multi-GPU MAX all-reduce)."""
+        out = torch.empty(1, dtype=torch.float32, device=self.device) if out is None else out
+        check(self.lib.b2rl_tree_stats(self._h, float(beta), None, out.data_ptr(), self._st()))
         return out
 
     def priorities(self, start: int = 0, n: int | None = None) -> torch.Tensor:

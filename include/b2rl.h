@@ -104,10 +104,21 @@ int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n, void* str
  *   idx_out   int64[n]  sampled slot ids (with replacement)
  *   prob_out  fp32[n]   p_i / sum(p)               (may be NULL)
  *   w_out     fp32[n]   (1/(N*prob))^beta / max_w  (may be NULL)
+ *   max_w_dev NULL: max_w is this shard's own max_j (N*prob_j)^-beta.  Non-NULL:
+ *             one device float used instead — the all-reduced MAX over the shards
+ *             of a multi-GPU replay (SURVEY.md §8e "priority-max reduction").
  * Sampling from an empty tree is an error. */
 int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t seed, uint64_t rng_offset,
-                     int64_t n, float beta, int64_t* idx_out_dev, float* prob_out_dev,
-                     float* w_out_dev, void* stream);
+                     int64_t n, float beta, const float* max_w_dev, int64_t* idx_out_dev,
+                     float* prob_out_dev, float* w_out_dev, void* stream);
+
+/* Same, but the uniforms come from the handle's DEVICE-RESIDENT Philox stream
+ * {seed, counter} (set with b2rl_replay_seed), and the counter is advanced by n
+ * on the stream afterwards — so the call can be captured in a CUDA graph and
+ * every replay draws fresh numbers.  Draw k of the call uses counter + k. */
+int b2rl_replay_seed(b2rl_replay* h, uint64_t seed, uint64_t counter, void* stream);
+int b2rl_tree_sample_stream(b2rl_replay* h, int64_t n, float beta, const float* max_w_dev,
+                            int64_t* idx_out_dev, float* prob_out_dev, float* w_out_dev, void* stream);
 
 /* The uniforms b2rl_tree_sample would draw for (seed, rng_offset) — lets a
  * test replay a device-RNG run through the oracle. */
@@ -124,8 +135,11 @@ int b2rl_tree_update(b2rl_replay* h, const int64_t* idx_dev, const float* vals_d
 
 /* PrioritizedMemory.total_prios (baseline/utils.py:359-360) and
  * PER.max_weight (baseline/PER.py:129-133).  stats_out_dev receives 3
- * doubles: {sum(p), min valid p, max IS weight for `beta`}. */
-int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev, void* stream);
+ * doubles: {sum(p), min valid p, max IS weight for `beta`}; max_w_out_dev (may be
+ * NULL) receives the max IS weight as one fp32 (the operand of the multi-GPU
+ * MAX all-reduce). */
+int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev, float* max_w_out_dev,
+                    void* stream);
 
 /* Tree.prior_torch (baseline/PER.py:17) read-back: priorities of slots
  * [start, start+n) as fp32. */

@@ -168,13 +168,15 @@ def test_philox_device_rng_matches_restatement(R):
     rep = R.DeviceReplay(4096, fields=())
     p = _rand_prios(np.random.default_rng(0), 4096)
     rep.build(_dev(p))
-    rep.seed = 0x1234ABCD5678
-    u = rep.philox_uniforms(rep.seed, 7, 1000).cpu().numpy()
-    np.testing.assert_array_equal(u, O.philox_u01(rep.seed, 7, 1000))
-    rep._rng_offset = 7
-    idx, _, _ = rep.sample(1000)            # device-drawn uniforms
+    seed = 0x1234ABCD5678
+    u = rep.philox_uniforms(seed, 7, 1000).cpu().numpy()
+    np.testing.assert_array_equal(u, O.philox_u01(seed, 7, 1000))
     t = O.SumTreeOracle(4096); t.build(p)
+    idx, _, _ = rep.sample_counter(seed, 7, 1000)          # stateless device-drawn uniforms
     np.testing.assert_array_equal(idx.cpu().numpy(), t.sample(u)[0])
+    rep.seed(seed, 7)                                       # device-resident stream: 600 + 400 draws
+    i1, _, _ = rep.sample(600); i2, _, _ = rep.sample(400)
+    np.testing.assert_array_equal(torch.cat([i1, i2]).cpu().numpy(), t.sample(u)[0])
     assert 0.45 < u.mean() < 0.55
     rep.close()
 
