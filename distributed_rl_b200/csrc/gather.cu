@@ -53,29 +53,36 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 // ----------------------------------------------------------------------------
 // Bulk gather.  Work item = (field, sample k, chunk c); a chunk is at most
-// GATHER_CHUNK bytes of one row.  One thread per CTA drives an S-stage ring:
+// GATHER_CHUNK bytes of one row.  Thread 0 of each CTA drives an S-stage ring:
 //   load(item) : cp.async.bulk global -> smem, completes on mbarrier[stage]
 //   store(item): cp.async.bulk smem -> global (bulk_group)
-// The SMs only issue descriptors; the data never touches the register file.
+// The SMs only issue descriptors; the payload never touches the register file.
+// Chunks are small (7 KiB) and the ring deep (30 stages) so that stores of the
+// first chunks overlap the loads of the later ones instead of a load phase
+// followed by a store phase.  Warp 1 copies the scalar fields (action, reward,
+// done, ...) of the CTA's share of the samples, so one launch assembles the
+// whole minibatch.
 // ----------------------------------------------------------------------------
-constexpr int GATHER_CHUNK = 28672;  // 28 KiB, >= one (4,84,84) uint8 frame stack (28 224 B)
-constexpr int GATHER_STAGES = 8;     // 8 x 28 KiB = 224 KiB of the 227 KiB SMEM
-constexpr int GATHER_MAX_ITEMS_CACHED = 512;
+constexpr int GATHER_CHUNK = 7168;   // 7 KiB; a (4,84,84) uint8 frame stack (28 224 B) = 4 chunks
+constexpr int GATHER_STAGES = 30;    // 30 x 7 KiB = 210 KiB of the 227 KiB SMEM
+constexpr int GATHER_LAG = 6;        // refill a stage once the store issued LAG items ago has drained it
+constexpr int GATHER_THREADS = 64;
 
 struct GatherField {
   const uint8_t* src;   // field base
   uint8_t* dst;         // output base
-  int64_t row_bytes;    // multiple of 16
+  int64_t row_bytes;    // multiple of 16 for bulk fields
   int32_t chunks;       // ceil(row_bytes / GATHER_CHUNK)
   int32_t pad;
 };
 struct GatherParams {
-  GatherField f[B2RL_MAX_FIELDS];
+  GatherField f[B2RL_MAX_FIELDS];    // bulk (TMA) fields
+  GatherField s[B2RL_MAX_FIELDS];    // small fields, copied by warp 1
   int32_t n_fields;
-  int32_t pad;
+  int32_t n_small;
   int64_t n;            // samples
   int64_t capacity;
-  int64_t items_per_sample;  // sum of chunks over fields
+  int64_t items_per_sample;  // sum of chunks over bulk fields
   int64_t total_items;
 };
 
@@ -95,18 +102,47 @@ __device__ __forceinline__ void gather_decode(const GatherParams& P, const int64
   dst = P.f[f].dst + k * P.f[f].row_bytes + off;
 }
 
-__global__ void __launch_bounds__(32, 1)
+__global__ void __launch_bounds__(GATHER_THREADS, 1)
 k_gather_bulk(const __grid_constant__ GatherParams P, const int64_t* __restrict__ idx) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar[GATHER_STAGES];
-  if (threadIdx.x != 0) return;  // a single thread drives the copy engine
+
+  if (threadIdx.x >= 32) {
+    // ---- warp 1: scalar fields of samples [k0, k1) ------------------------------------
+    const int lane = threadIdx.x - 32;
+    const int64_t per = (P.n + gridDim.x - 1) / gridDim.x;
+    const int64_t k0 = (int64_t)blockIdx.x * per;
+    const int64_t k1 = (k0 + per < P.n) ? k0 + per : P.n;
+    for (int f = 0; f < P.n_small; ++f) {
+      const int64_t rb = P.s[f].row_bytes;
+      if ((rb & 3) == 0) {
+        const int64_t words = rb >> 2;
+        for (int64_t u = lane; u < (k1 - k0) * words; u += 32) {
+          const int64_t k = k0 + u / words, w = u % words;
+          int64_t row = idx[k];
+          row = row < 0 ? 0 : (row >= P.capacity ? P.capacity - 1 : row);
+          reinterpret_cast<uint32_t*>(P.s[f].dst)[k * words + w] =
+              reinterpret_cast<const uint32_t*>(P.s[f].src)[row * words + w];
+        }
+      } else {
+        for (int64_t u = lane; u < (k1 - k0) * rb; u += 32) {
+          const int64_t k = k0 + u / rb, b = u % rb;
+          int64_t row = idx[k];
+          row = row < 0 ? 0 : (row >= P.capacity ? P.capacity - 1 : row);
+          P.s[f].dst[k * rb + b] = P.s[f].src[row * rb + b];
+        }
+      }
+    }
+    return;
+  }
+  if (threadIdx.x != 0 || P.total_items == 0) return;  // a single thread drives the copy engine
   for (int s = 0; s < GATHER_STAGES; ++s) mbar_init(&bar[s], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   // items of this CTA: a contiguous range, so consecutive items share idx[] cache lines
   const int64_t per_cta = (P.total_items + gridDim.x - 1) / gridDim.x;
-  const int64_t first = (int64_t)blockIdx.x * per_cta, stride = 1;
+  const int64_t first = (int64_t)blockIdx.x * per_cta;
   const int64_t my_items =
       (P.total_items > first) ? ((P.total_items - first < per_cta) ? P.total_items - first : per_cta) : 0;
   uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
@@ -115,26 +151,27 @@ k_gather_bulk(const __grid_constant__ GatherParams P, const int64_t* __restrict_
   const int64_t pre = my_items < GATHER_STAGES ? my_items : GATHER_STAGES;
   for (int64_t t = 0; t < pre; ++t) {
     const uint8_t* src; uint8_t* dst; uint32_t bytes;
-    gather_decode(P, idx, first + t * stride, src, dst, bytes);
+    gather_decode(P, idx, first + t, src, dst, bytes);
     mbar_expect_tx(&bar[t], bytes);
     bulk_g2s(smem + (size_t)t * GATHER_CHUNK, src, bytes, &bar[t]);
   }
   for (int64_t t = 0; t < my_items; ++t) {
     const int s = (int)(t % GATHER_STAGES);
     const uint8_t* src; uint8_t* dst; uint32_t bytes;
-    gather_decode(P, idx, first + t * stride, src, dst, bytes);
+    gather_decode(P, idx, first + t, src, dst, bytes);
     mbar_wait(&bar[s], (phase_bits >> s) & 1u);
     phase_bits ^= (1u << s);
     bulk_s2g(dst, smem + (size_t)s * GATHER_CHUNK, bytes);
     bulk_commit();
-    // refill the stage used by the PREVIOUS item once its store has drained SMEM
-    if (t >= 1) {
-      const int64_t nt = t - 1 + GATHER_STAGES;
+    // refill the stage used LAG items ago once its store has drained SMEM
+    if (t >= GATHER_LAG) {
+      const int64_t ot = t - GATHER_LAG;              // item whose stage is recycled
+      const int64_t nt = ot + GATHER_STAGES;          // item that takes it over
       if (nt < my_items) {
-        bulk_wait_read<1>();  // all but the newest store group have finished reading SMEM
-        const int ps = (int)((t - 1) % GATHER_STAGES);
+        bulk_wait_read<GATHER_LAG>();                 // all but the newest LAG store groups have read SMEM
+        const int ps = (int)(ot % GATHER_STAGES);
         const uint8_t* nsrc; uint8_t* ndst; uint32_t nbytes;
-        gather_decode(P, idx, first + nt * stride, nsrc, ndst, nbytes);
+        gather_decode(P, idx, first + nt, nsrc, ndst, nbytes);
         mbar_expect_tx(&bar[ps], nbytes);
         bulk_g2s(smem + (size_t)ps * GATHER_CHUNK, nsrc, nbytes, &bar[ps]);
       }
@@ -239,32 +276,38 @@ extern "C" int b2rl_replay_gather(b2rl_replay* h, const int64_t* idx_dev, int64_
   GatherParams P{};
   P.n = n;
   P.capacity = h->capacity;
-  int nb = 0;
+  int nb = 0, ns = 0;
   for (int f = 0; f < h->n_fields; ++f) {
     uint8_t* out = (uint8_t*)out_fields_dev[f];
     if (out == nullptr) continue;
     const int64_t rb = h->field_bytes[f];
-    const bool bulk_ok = gather_mode() == 0 && (rb % 16 == 0) && rb >= 1024 &&
-                         ((uintptr_t)out % 16 == 0) && ((uintptr_t)h->field[f] % 16 == 0);
-    if (bulk_ok) {
+    const bool big = rb >= 1024;
+    const bool aligned16 = (rb % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)h->field[f] % 16 == 0);
+    if (big && aligned16 && gather_mode() == 0) {
       P.f[nb].src = h->field[f];
       P.f[nb].dst = out;
       P.f[nb].row_bytes = rb;
       P.f[nb].chunks = (int32_t)((rb + GATHER_CHUNK - 1) / GATHER_CHUNK);
       P.items_per_sample += P.f[nb].chunks;
       ++nb;
-    } else if (rb % 16 == 0 && rb >= 1024 && ((uintptr_t)out % 16 == 0)) {
+    } else if (big && aligned16) {
       k_gather_ldg<<<(unsigned)n, 256, 0, st>>>(h->field[f], out, rb, idx_dev, n, h->capacity);
       count_launch();
+    } else if (!big && ((rb % 4 != 0) || (((uintptr_t)out % 4 == 0) && ((uintptr_t)h->field[f] % 4 == 0)))) {
+      P.s[ns].src = h->field[f];
+      P.s[ns].dst = out;
+      P.s[ns].row_bytes = rb;
+      ++ns;
     } else {
-      const int64_t units = (rb % 4 == 0) ? n * (rb / 4) : n * rb;
+      const int64_t units = (rb % 4 == 0 && (uintptr_t)out % 4 == 0) ? n * (rb / 4) : n * rb;
       k_gather_small<<<(unsigned)((units + 255) / 256), 256, 0, st>>>(h->field[f], out, rb, idx_dev, n,
                                                                      h->capacity);
       count_launch();
     }
   }
-  if (nb > 0) {
+  if (nb > 0 || ns > 0) {
     P.n_fields = nb;
+    P.n_small = ns;
     P.total_items = P.items_per_sample * n;
     static int sms[64] = {0};
     static bool attr_set[64] = {false};
@@ -277,8 +320,9 @@ extern "C" int b2rl_replay_gather(b2rl_replay* h, const int64_t* idx_dev, int64_
       attr_set[dev & 63] = true;
     }
     int64_t grid = sms[dev & 63];
-    if (grid > P.total_items) grid = P.total_items;
-    k_gather_bulk<<<(unsigned)grid, 32, smem_bytes, st>>>(P, idx_dev);
+    const int64_t work = P.total_items > n ? P.total_items : n;
+    if (grid > work) grid = work;
+    k_gather_bulk<<<(unsigned)grid, GATHER_THREADS, smem_bytes, st>>>(P, idx_dev);
     count_launch();
   }
   B2RL_CHECK_LAUNCH();

@@ -13,6 +13,10 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 
 namespace b2rl {
 
@@ -234,6 +238,110 @@ k_update_climb(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
   }
 }
 
+// ----------------------------------------------------------------------------
+// Small-batch update (n <= 512 per launch): ONE CTA, no atomics, no scratch.
+//   1. stable radix sort of the leaf ids (CUB) -> duplicates are adjacent and the
+//      last occurrence (the winner) is the last of its run
+//   2. every thread prefetches the `levels` sibling nodes of its path in one go
+//      (independent addresses: one L2 round trip instead of one per level)
+//   3. level by level in shared memory: threads sharing a node form a contiguous
+//      group [lo, hi); the sibling node is either the adjacent group (touched by
+//      this batch -> take its fresh value from SMEM) or untouched (-> prefetched
+//      value); parent = left + right; groups merge; the group leader writes the
+//      node back.  ~150 cycles per level instead of two fenced L2 atomics.
+// Same final state as the sequential reference writes (path-independent reduce).
+// ----------------------------------------------------------------------------
+constexpr int US_THREADS = 512;
+constexpr int US_MAX_LEVELS = 24;
+
+__global__ void __launch_bounds__(US_THREADS, 1)
+k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
+                const float* __restrict__ vals, float const_val, int n, double* __restrict__ sum,
+                float* __restrict__ minv, int64_t cap2, int levels) {
+  using Sort = cub::BlockRadixSort<uint32_t, US_THREADS, 1, float>;
+  __shared__ typename Sort::TempStorage sort_tmp;
+  __shared__ uint32_t s_leaf[US_THREADS];
+  __shared__ float s_valf[US_THREADS];
+  __shared__ double s_sum[US_THREADS];
+  __shared__ float s_min[US_THREADS];
+  __shared__ uint16_t s_lo[US_THREADS], s_hi[US_THREADS], s_end[US_THREADS];
+
+  const int t = threadIdx.x;
+  const uint32_t kInvalid = 1u << levels;   // sorts after every valid leaf id (< 2^levels)
+  uint32_t key[1] = {kInvalid};
+  float val[1] = {0.0f};
+  if (t < n) {
+    const int64_t j = upd_index(idx, ring_start, capacity, t);
+    if (j >= 0 && j < capacity) { key[0] = (uint32_t)j; val[0] = vals ? vals[t] : const_val; }
+  }
+  Sort(sort_tmp).Sort(key, val, 0, levels + 1);   // stable: equal leaves keep batch order
+  const uint32_t leaf = key[0];
+  const bool valid = leaf < kInvalid;
+  s_leaf[t] = leaf;
+  s_valf[t] = val[0];
+  const int nvalid = __syncthreads_count(valid);  // also publishes s_leaf / s_valf
+
+  // prefetch the sibling of every node on my path (depth `levels` = leaves ... depth 1)
+  double pre_sum[US_MAX_LEVELS];
+  float pre_min[US_MAX_LEVELS];
+#pragma unroll
+  for (int l = 0; l < US_MAX_LEVELS; ++l) {
+    if (valid && l < levels) {
+      const int64_t node = ((cap2 + (int64_t)leaf) >> l) ^ 1;   // heap index of the sibling
+      pre_sum[l] = __ldcg(sum + node);
+      pre_min[l] = __ldcg(minv + node);
+    } else { pre_sum[l] = 0.0; pre_min[l] = INFINITY; }
+  }
+
+  // runs of equal leaves: [lo, hi)
+  const bool head = valid && (t == 0 || s_leaf[t - 1] != leaf);
+  const bool tail = valid && (t == nvalid - 1 || s_leaf[t + 1] != leaf);
+  int lo;
+  {
+    using Scan = cub::BlockScan<int, US_THREADS>;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    Scan(scan_tmp).InclusiveScan(head ? t : 0, lo, cub::Max());
+  }
+  if (tail) s_end[lo] = (uint16_t)(t + 1);
+  __syncthreads();
+  int hi = valid ? s_end[lo] : 0;
+  const float vwin = valid ? s_valf[hi - 1] : 0.0f;          // last writer wins
+  double cur_sum = (double)vwin;
+  float cur_min = (vwin > 0.0f) ? vwin : INFINITY;
+  if (valid && t == lo) {
+    sum[cap2 + leaf] = cur_sum;
+    minv[cap2 + leaf] = cur_min;
+  }
+#pragma unroll
+  for (int l = 0; l < US_MAX_LEVELS; ++l) {
+    if (l >= levels) break;
+    s_sum[t] = cur_sum; s_min[t] = cur_min; s_lo[t] = (uint16_t)lo; s_hi[t] = (uint16_t)hi;
+    __syncthreads();
+    if (valid) {
+      const uint32_t node = leaf >> l;          // index within its level
+      double sib_sum = pre_sum[l];
+      float sib_min = pre_min[l];
+      if ((node & 1u) == 0u) {
+        if (hi < nvalid && (s_leaf[hi] >> l) == node + 1u) {
+          sib_sum = s_sum[hi]; sib_min = s_min[hi]; hi = s_hi[hi];
+        }
+      } else {
+        if (lo > 0 && (s_leaf[lo - 1] >> l) == node - 1u) {
+          sib_sum = s_sum[lo - 1]; sib_min = s_min[lo - 1]; lo = s_lo[lo - 1];
+        }
+      }
+      cur_sum = cur_sum + sib_sum;              // fl64(left + right); + is commutative
+      cur_min = fminf(cur_min, sib_min);
+    }
+    __syncthreads();
+    if (valid && t == lo) {
+      const int64_t parent = (cap2 + (int64_t)leaf) >> (l + 1);
+      sum[parent] = cur_sum;
+      minv[parent] = cur_min;
+    }
+  }
+}
+
 }  // namespace b2rl
 
 using namespace b2rl;
@@ -245,6 +353,24 @@ static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n +
 int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_start,
                           const float* vals_dev, float const_val, int64_t n, cudaStream_t st) {
   if (n == 0) return B2RL_OK;
+  static int force_atomic = -1;
+  if (force_atomic < 0) {
+    const char* e = getenv("B2RL_UPDATE");
+    force_atomic = (e && e[0] == 'a') ? 1 : 0;   // B2RL_UPDATE=atomic forces the scalable path
+  }
+  if (!force_atomic && n <= 8 * US_THREADS && h->levels <= US_MAX_LEVELS) {
+    // chunks are applied in stream order, so last-writer-wins also holds across chunks
+    for (int64_t off = 0; off < n; off += US_THREADS) {
+      const int m = (int)((n - off < US_THREADS) ? (n - off) : US_THREADS);
+      k_update_sorted<<<1, US_THREADS, 0, st>>>(idx_dev ? idx_dev + off : nullptr,
+                                                (ring_start + off) % h->capacity, h->capacity,
+                                                vals_dev ? vals_dev + off : nullptr, const_val, m, h->sum,
+                                                h->minv, h->cap2, h->levels);
+      count_launch();
+    }
+    B2RL_CHECK_LAUNCH();
+    return B2RL_OK;
+  }
   const unsigned g = grid_for(n, UPD_THREADS);
   k_update_tag<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag);
   k_update_write<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, vals_dev, const_val, n,
