@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--log2n", type=int, default=20, help="log2 of replay slots per GPU")
     ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--nchw", action="store_true", help="keep the network in NCHW (default: channels_last)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=6)
     return ap.parse_args()
@@ -187,7 +188,8 @@ def main():
     lib = _lib.load()
 
     N, B = 1 << args.log2n, args.batch
-    cfg = ApexConfig(BATCHSIZE=B, REPLAY_MEMORY_LEN=N, BUFFER_SIZE=0, LEARNER_DEVICE=str(dev))
+    cfg = ApexConfig(BATCHSIZE=B, REPLAY_MEMORY_LEN=N, BUFFER_SIZE=0, LEARNER_DEVICE=str(dev),
+                     CHANNELS_LAST=not args.nchw)
     torch.manual_seed(0)
     learner = Learner(cfg, connect=None, start_replay=False)
     if world > 1:   # identical initial weights on every rank
@@ -325,8 +327,15 @@ def main():
                 "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "clocks": clock_info,
                 "cuda_graph": use_graph, "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that hold NCCL kernels make destroy_process_group()/interpreter teardown hang:
+        # drop them, drain the device, leave together, and exit without running destructors.
+        learner._graph = None
+        del gg
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -49,6 +49,7 @@ class ApexConfig:
         "name": "rmsprop", "lr": 0.0000625, "eps": 1.5e-7, "decay": 0, "alpha": 0.95, "momentum": 0,
         "centered": True})
     MODEL: dict = field(default_factory=lambda: default_apex_model())
+    CHANNELS_LAST: bool = True      # NHWC activations/weights: cuDNN's TF32 kernels skip their layout transposes
 
     @staticmethod
     def from_configuration():
@@ -235,6 +236,10 @@ class Learner:
     def build_model(self):
         self.model = GraphAgent(self.cfg.MODEL).to(self.device)
         self.target_model = GraphAgent(self.cfg.MODEL).to(self.device)
+        self._mf = torch.channels_last if self.cfg.CHANNELS_LAST else torch.contiguous_format
+        if self.cfg.CHANNELS_LAST:
+            self.model.to(memory_format=torch.channels_last)
+            self.target_model.to(memory_format=torch.channels_last)
 
     def build_optim(self):
         self.optim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
@@ -248,8 +253,8 @@ class Learner:
         return torch.as_tensor(x).to(device=self.device, dtype=dtype, non_blocking=True)
 
     def _forward_backward(self, state, action, reward, next_state, done, weight):
-        s = state.to(torch.float32) / 255.0            # :61-63 (on the device: no fp32 H2D)
-        ns = next_state.to(torch.float32) / 255.0      # :65-67
+        s = (state.to(torch.float32) / 255.0).contiguous(memory_format=self._mf)        # :61-63, on the device
+        ns = (next_state.to(torch.float32) / 255.0).contiguous(memory_format=self._mf)  # :65-67
         q = self.model.forward([s])[0]                 # :78
         with torch.no_grad():
             qn_target = self.target_model.forward([ns])[0]   # :85

@@ -63,16 +63,14 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // done, ...) of the CTA's share of the samples, so one launch assembles the
 // whole minibatch.
 // ----------------------------------------------------------------------------
-constexpr int GATHER_CHUNK = 7168;   // 7 KiB; a (4,84,84) uint8 frame stack (28 224 B) = 4 chunks
-constexpr int GATHER_STAGES = 30;    // 30 x 7 KiB = 210 KiB of the 227 KiB SMEM
-constexpr int GATHER_LAG = 6;        // refill a stage once the store issued LAG items ago has drained it
 constexpr int GATHER_THREADS = 64;
+constexpr int GATHER_SMEM = 229376;  // 224 KiB ring; stages = GATHER_SMEM / CHUNK
 
 struct GatherField {
   const uint8_t* src;   // field base
   uint8_t* dst;         // output base
   int64_t row_bytes;    // multiple of 16 for bulk fields
-  int32_t chunks;       // ceil(row_bytes / GATHER_CHUNK)
+  int32_t chunks;       // ceil(row_bytes / CHUNK)
   int32_t pad;
 };
 struct GatherParams {
@@ -86,26 +84,49 @@ struct GatherParams {
   int64_t total_items;
 };
 
-__device__ __forceinline__ void gather_decode(const GatherParams& P, const int64_t* __restrict__ idx,
-                                              int64_t item, const uint8_t*& src, uint8_t*& dst,
-                                              uint32_t& bytes) {
-  const int64_t k = item / P.items_per_sample;
-  int32_t r = (int32_t)(item - k * P.items_per_sample);
-  int f = 0;
-  while (r >= P.f[f].chunks) { r -= P.f[f].chunks; ++f; }
-  int64_t row = idx[k];
-  row = row < 0 ? 0 : (row >= P.capacity ? P.capacity - 1 : row);
-  const int64_t off = (int64_t)r * GATHER_CHUNK;
-  const int64_t rem = P.f[f].row_bytes - off;
-  bytes = (uint32_t)(rem < GATHER_CHUNK ? rem : GATHER_CHUNK);
-  src = P.f[f].src + row * P.f[f].row_bytes + off;
-  dst = P.f[f].dst + k * P.f[f].row_bytes + off;
-}
+// Walks the CTA's contiguous item range (sample-major, then field, then chunk) without divisions.
+template <int CHUNK>
+struct ItemCursor {
+  int64_t k, row;
+  int32_t f, c;
+  __device__ __forceinline__ void init(const GatherParams& P, const int64_t* __restrict__ idx, int64_t item) {
+    k = item / P.items_per_sample;
+    int32_t r = (int32_t)(item - k * P.items_per_sample);
+    f = 0;
+    while (r >= P.f[f].chunks) { r -= P.f[f].chunks; ++f; }
+    c = r;
+    row = clamp_row(P, idx[k]);
+  }
+  static __device__ __forceinline__ int64_t clamp_row(const GatherParams& P, int64_t r) {
+    return r < 0 ? 0 : (r >= P.capacity ? P.capacity - 1 : r);
+  }
+  __device__ __forceinline__ void get(const GatherParams& P, const uint8_t*& src, uint8_t*& dst,
+                                      uint32_t& bytes) const {
+    const int64_t off = (int64_t)c * CHUNK;
+    const int64_t rem = P.f[f].row_bytes - off;
+    bytes = (uint32_t)(rem < CHUNK ? rem : CHUNK);
+    src = P.f[f].src + row * P.f[f].row_bytes + off;
+    dst = P.f[f].dst + k * P.f[f].row_bytes + off;
+  }
+  __device__ __forceinline__ void next(const GatherParams& P, const int64_t* __restrict__ idx, bool more) {
+    if (++c == P.f[f].chunks) {
+      c = 0;
+      if (++f == P.n_fields) {
+        f = 0;
+        ++k;
+        if (more) row = clamp_row(P, idx[k]);
+      }
+    }
+  }
+};
 
+template <int CHUNK, int LAG>
 __global__ void __launch_bounds__(GATHER_THREADS, 1)
 k_gather_bulk(const __grid_constant__ GatherParams P, const int64_t* __restrict__ idx) {
+  constexpr int STAGES = GATHER_SMEM / CHUNK;
+  static_assert(STAGES <= 32 && STAGES > LAG + 1, "ring geometry");
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar[GATHER_STAGES];
+  __shared__ __align__(8) uint64_t bar[STAGES];
 
   if (threadIdx.x >= 32) {
     // ---- warp 1: scalar fields of samples [k0, k1) ------------------------------------
@@ -136,45 +157,53 @@ k_gather_bulk(const __grid_constant__ GatherParams P, const int64_t* __restrict_
     return;
   }
   if (threadIdx.x != 0 || P.total_items == 0) return;  // a single thread drives the copy engine
-  for (int s = 0; s < GATHER_STAGES; ++s) mbar_init(&bar[s], 1);
+  for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   // items of this CTA: a contiguous range, so consecutive items share idx[] cache lines
   const int64_t per_cta = (P.total_items + gridDim.x - 1) / gridDim.x;
   const int64_t first = (int64_t)blockIdx.x * per_cta;
-  const int64_t my_items =
-      (P.total_items > first) ? ((P.total_items - first < per_cta) ? P.total_items - first : per_cta) : 0;
+  if (first >= P.total_items) return;
+  const int64_t my_items = (P.total_items - first < per_cta) ? P.total_items - first : per_cta;
   uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
 
+  ItemCursor<CHUNK> ld, stc;   // load cursor runs ahead of the store cursor
+  ld.init(P, idx, first);
+  stc = ld;
+  int64_t loaded = 0;
   // prologue: fill the ring
-  const int64_t pre = my_items < GATHER_STAGES ? my_items : GATHER_STAGES;
-  for (int64_t t = 0; t < pre; ++t) {
+  const int64_t pre = my_items < STAGES ? my_items : STAGES;
+  for (; loaded < pre; ++loaded) {
     const uint8_t* src; uint8_t* dst; uint32_t bytes;
-    gather_decode(P, idx, first + t, src, dst, bytes);
-    mbar_expect_tx(&bar[t], bytes);
-    bulk_g2s(smem + (size_t)t * GATHER_CHUNK, src, bytes, &bar[t]);
+    ld.get(P, src, dst, bytes);
+    mbar_expect_tx(&bar[loaded], bytes);
+    bulk_g2s(smem + (size_t)loaded * CHUNK, src, bytes, &bar[loaded]);
+    ld.next(P, idx, loaded + 1 < my_items);
   }
+  int s = 0;            // stage of item t
+  int rs = 0;           // stage to recycle next (item t - LAG)
   for (int64_t t = 0; t < my_items; ++t) {
-    const int s = (int)(t % GATHER_STAGES);
     const uint8_t* src; uint8_t* dst; uint32_t bytes;
-    gather_decode(P, idx, first + t, src, dst, bytes);
+    stc.get(P, src, dst, bytes);
     mbar_wait(&bar[s], (phase_bits >> s) & 1u);
     phase_bits ^= (1u << s);
-    bulk_s2g(dst, smem + (size_t)s * GATHER_CHUNK, bytes);
+    bulk_s2g(dst, smem + (size_t)s * CHUNK, bytes);
     bulk_commit();
+    stc.next(P, idx, t + 1 < my_items);
+    if (++s == STAGES) s = 0;
     // refill the stage used LAG items ago once its store has drained SMEM
-    if (t >= GATHER_LAG) {
-      const int64_t ot = t - GATHER_LAG;              // item whose stage is recycled
-      const int64_t nt = ot + GATHER_STAGES;          // item that takes it over
-      if (nt < my_items) {
-        bulk_wait_read<GATHER_LAG>();                 // all but the newest LAG store groups have read SMEM
-        const int ps = (int)(ot % GATHER_STAGES);
+    if (t >= LAG) {
+      if (loaded < my_items) {
+        bulk_wait_read<LAG>();   // all but the newest LAG store groups have finished reading SMEM
         const uint8_t* nsrc; uint8_t* ndst; uint32_t nbytes;
-        gather_decode(P, idx, first + nt, nsrc, ndst, nbytes);
-        mbar_expect_tx(&bar[ps], nbytes);
-        bulk_g2s(smem + (size_t)ps * GATHER_CHUNK, nsrc, nbytes, &bar[ps]);
+        ld.get(P, nsrc, ndst, nbytes);
+        mbar_expect_tx(&bar[rs], nbytes);
+        bulk_g2s(smem + (size_t)rs * CHUNK, nsrc, nbytes, &bar[rs]);
+        ++loaded;
+        ld.next(P, idx, loaded < my_items);
       }
+      if (++rs == STAGES) rs = 0;
     }
   }
   bulk_wait_all();
@@ -255,6 +284,16 @@ using namespace b2rl;
 int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_start,
                           const float* vals_dev, float const_val, int64_t n, cudaStream_t st);
 
+static int gather_chunk() {
+  static int chunk = -1;
+  if (chunk < 0) {
+    const char* e = getenv("B2RL_GATHER_CHUNK");   // 28672 (8 stages) | 14336 (16) | 7168 (32 -> 28 used)
+    chunk = e ? atoi(e) : 14336;
+    if (chunk != 28672 && chunk != 14336 && chunk != 8192) chunk = 14336;
+  }
+  return chunk;
+}
+
 static int gather_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -287,7 +326,7 @@ extern "C" int b2rl_replay_gather(b2rl_replay* h, const int64_t* idx_dev, int64_
       P.f[nb].src = h->field[f];
       P.f[nb].dst = out;
       P.f[nb].row_bytes = rb;
-      P.f[nb].chunks = (int32_t)((rb + GATHER_CHUNK - 1) / GATHER_CHUNK);
+      P.f[nb].chunks = (int32_t)((rb + gather_chunk() - 1) / gather_chunk());
       P.items_per_sample += P.f[nb].chunks;
       ++nb;
     } else if (big && aligned16) {
@@ -312,17 +351,25 @@ extern "C" int b2rl_replay_gather(b2rl_replay* h, const int64_t* idx_dev, int64_
     static int sms[64] = {0};
     static bool attr_set[64] = {false};
     const int dev = h->device;
-    const size_t smem_bytes = (size_t)GATHER_STAGES * GATHER_CHUNK;
+    const size_t smem_bytes = (size_t)GATHER_SMEM;
     if (!attr_set[dev & 63]) {
       B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-      B2RL_CUDA(cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      B2RL_CUDA(cudaFuncSetAttribute(k_gather_bulk<28672, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+      B2RL_CUDA(cudaFuncSetAttribute(k_gather_bulk<14336, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+      B2RL_CUDA(cudaFuncSetAttribute(k_gather_bulk<8192, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes));
       attr_set[dev & 63] = true;
     }
     int64_t grid = sms[dev & 63];
     const int64_t work = P.total_items > n ? P.total_items : n;
     if (grid > work) grid = work;
-    k_gather_bulk<<<(unsigned)grid, GATHER_THREADS, smem_bytes, st>>>(P, idx_dev);
+    switch (gather_chunk()) {
+      case 28672: k_gather_bulk<28672, 1><<<(unsigned)grid, GATHER_THREADS, smem_bytes, st>>>(P, idx_dev); break;
+      case 8192:  k_gather_bulk<8192, 6><<<(unsigned)grid, GATHER_THREADS, smem_bytes, st>>>(P, idx_dev); break;
+      default:    k_gather_bulk<14336, 3><<<(unsigned)grid, GATHER_THREADS, smem_bytes, st>>>(P, idx_dev); break;
+    }
     count_launch();
   }
   B2RL_CHECK_LAUNCH();

@@ -15,7 +15,6 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 
 namespace b2rl {
@@ -240,7 +239,7 @@ k_update_climb(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
 
 // ----------------------------------------------------------------------------
 // Small-batch update (n <= 512 per launch): ONE CTA, no atomics, no scratch.
-//   1. stable radix sort of the leaf ids (CUB) -> duplicates are adjacent and the
+//   1. bitonic sort of (leaf id, batch position) -> duplicates are adjacent and the
 //      last occurrence (the winner) is the last of its run
 //   2. every thread prefetches the `levels` sibling nodes of its path in one go
 //      (independent addresses: one L2 round trip instead of one per level)
@@ -258,8 +257,7 @@ __global__ void __launch_bounds__(US_THREADS, 1)
 k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
                 const float* __restrict__ vals, float const_val, int n, double* __restrict__ sum,
                 float* __restrict__ minv, int64_t cap2, int levels) {
-  using Sort = cub::BlockRadixSort<uint32_t, US_THREADS, 1, float>;
-  __shared__ typename Sort::TempStorage sort_tmp;
+  __shared__ uint64_t s_key[US_THREADS];
   __shared__ uint32_t s_leaf[US_THREADS];
   __shared__ float s_valf[US_THREADS];
   __shared__ double s_sum[US_THREADS];
@@ -267,18 +265,38 @@ k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t cap
   __shared__ uint16_t s_lo[US_THREADS], s_hi[US_THREADS], s_end[US_THREADS];
 
   const int t = threadIdx.x;
-  const uint32_t kInvalid = 1u << levels;   // sorts after every valid leaf id (< 2^levels)
-  uint32_t key[1] = {kInvalid};
-  float val[1] = {0.0f};
+  // key = leaf << 9 | batch position: ascending sort puts duplicates of a leaf next to
+  // each other with the LAST occurrence last; invalid entries (all ones) go to the end.
+  uint64_t key = ~0ULL;
   if (t < n) {
     const int64_t j = upd_index(idx, ring_start, capacity, t);
-    if (j >= 0 && j < capacity) { key[0] = (uint32_t)j; val[0] = vals ? vals[t] : const_val; }
+    if (j >= 0 && j < capacity) key = ((uint64_t)j << 9) | (uint64_t)t;
   }
-  Sort(sort_tmp).Sort(key, val, 0, levels + 1);   // stable: equal leaves keep batch order
-  const uint32_t leaf = key[0];
-  const bool valid = leaf < kInvalid;
+  // block-wide bitonic sort, one key per thread: strides < 32 by warp shuffle, the rest via SMEM
+#pragma unroll
+  for (int size = 2; size <= US_THREADS; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      uint64_t other;
+      if (stride >= 32) {
+        s_key[t] = key;
+        __syncthreads();
+        other = s_key[t ^ stride];
+        __syncthreads();
+      } else {
+        other = __shfl_xor_sync(0xffffffffu, key, stride);
+      }
+      const bool up = (t & size) == 0;
+      const bool lower = (t & stride) == 0;
+      const bool take_min = (lower == up);
+      const uint64_t mn = key < other ? key : other, mx = key < other ? other : key;
+      key = take_min ? mn : mx;
+    }
+  }
+  const bool valid = key != ~0ULL;
+  const uint32_t leaf = valid ? (uint32_t)(key >> 9) : 0xFFFFFFFFu;
   s_leaf[t] = leaf;
-  s_valf[t] = val[0];
+  s_valf[t] = valid ? (vals ? vals[(int)(key & 511u)] : const_val) : 0.0f;
   const int nvalid = __syncthreads_count(valid);  // also publishes s_leaf / s_valf
 
   // prefetch the sibling of every node on my path (depth `levels` = leaves ... depth 1)
@@ -358,7 +376,7 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
     const char* e = getenv("B2RL_UPDATE");
     force_atomic = (e && e[0] == 'a') ? 1 : 0;   // B2RL_UPDATE=atomic forces the scalable path
   }
-  if (!force_atomic && n <= 8 * US_THREADS && h->levels <= US_MAX_LEVELS) {
+  if (!force_atomic && n <= 2 * US_THREADS && h->levels <= US_MAX_LEVELS) {
     // chunks are applied in stream order, so last-writer-wins also holds across chunks
     for (int64_t off = 0; off < n; off += US_THREADS) {
       const int m = (int)((n - off < US_THREADS) ? (n - off) : US_THREADS);

@@ -110,4 +110,4 @@ def test_fused_graph_step_equals_eager_step(apex):
     for a, b in zip(pe, pg):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=5e-5)  # cuDNN picks algos per call
     assert (te != tg).float().mean() < 0.01       # same slots updated with (nearly) the same priorities
-    assert le == lg and le >= 6                   # sample+advance, gather(2), target, update(3)
+    assert le == lg and le >= 5                   # sample + rng advance, gather, target, update
