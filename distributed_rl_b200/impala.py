@@ -1,0 +1,155 @@
+"""IMPALA learner side with the reference's surface (IMPALA/ReplayMemory.py:14-85,
+IMPALA/Learner.py:17-297).  Rollouts (T+1 frames, T actions / behaviour probs /
+rewards, done) live in HBM; sampling is uniform WITHOUT replacement per call like
+baseline/utils.py ReplayMemory.sample (:310-315); the V-trace backward scan
+(:176-200, a Python loop of ~10 tiny kernels per step in the reference) is one
+launch of b2rl_vtrace."""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+
+import torch
+
+from . import replay as R
+from .agent import GraphAgent
+from .apex import make_optimizer
+
+
+def default_impala_model() -> dict:
+    """cfg/impala.json:24-52 (configuration values)."""
+    return {
+        "module00": {"netCat": "CNN2D", "iSize": 4, "nLayer": 3, "fSize": [8, 4, -1], "nUnit": [16, 32],
+                     "padding": [0, 0], "stride": [4, 2], "act": ["relu", "relu"], "BN": [False] * 3,
+                     "linear": True, "input": [0], "prior": 0},
+        "module01": {"netCat": "MLP", "iSize": 2592, "nLayer": 2, "fSize": [256, 7], "act": ["relu", "linear"],
+                     "BN": [False, False], "prior": 1, "prevNodeNames": ["module00"], "output": True},
+    }
+
+
+@dataclass
+class ImpalaConfig:
+    BATCHSIZE: int = 32
+    ACTION_SIZE: int = 6
+    GAMMA: float = 0.99
+    C_LAMBDA: float = 1
+    C_VALUE: float = 1.0
+    P_VALUE: float = 1.0
+    ENTROPY_R: float = 0.01
+    UNROLL_STEP: int = 20
+    REPLAY_MEMORY_LEN: int = 10000
+    BUFFER_SIZE: int = 9999
+    LEARNER_DEVICE: str = "cuda:0"
+    REDIS_SERVER: str = "localhost"
+    OPTIM_INFO: dict = field(default_factory=lambda: {"name": "rmsprop", "lr": 6e-4, "decay": 0})
+    MODEL: dict = field(default_factory=default_impala_model)
+
+    @staticmethod
+    def from_configuration():
+        import configuration as C
+        names = ("BATCHSIZE", "ACTION_SIZE", "GAMMA", "C_LAMBDA", "C_VALUE", "P_VALUE", "ENTROPY_R", "UNROLL_STEP",
+                 "REPLAY_MEMORY_LEN", "BUFFER_SIZE", "LEARNER_DEVICE", "REDIS_SERVER", "OPTIM_INFO", "MODEL")
+        return ImpalaConfig(**{k: getattr(C, k) for k in names})
+
+
+class Replay(threading.Thread):
+    """IMPALA/ReplayMemory.py Replay: batch = (s[T+1,B,28224], a[T,B], mu[T,B], r[T,B], done[B])."""
+
+    def __init__(self, cfg: ImpalaConfig | None = None, connect=None):
+        super().__init__(daemon=True)
+        self.cfg = cfg or ImpalaConfig.from_configuration()
+        self.device = torch.device(self.cfg.LEARNER_DEVICE)
+        self.store = R.DeviceReplay(self.cfg.REPLAY_MEMORY_LEN, R.impala_fields(self.cfg.UNROLL_STEP), self.device)
+        self.deque = []
+        self._connect = connect
+
+    def push_arrays(self, s, a, mu, r, done):
+        n = torch.as_tensor(done).numel()
+        self.store.push([s, a, mu, r, done], torch.ones(n))     # uniform replay: unit priorities
+
+    def bufferSave(self, m: int = 1):
+        """IMPALA/ReplayMemory.py:30-54 with random.sample's no-replacement semantics."""
+        B, size = self.cfg.BATCHSIZE, len(self.store)
+        idx = torch.randperm(size, device=self.device)[:B * m]
+        b = self.store.gather(idx)
+        for k in range(m):
+            sl = slice(k * B, (k + 1) * B)
+            self.deque.append((b["state"][sl].transpose(0, 1).contiguous(), b["action"][sl].t().contiguous(),
+                               b["mu"][sl].t().contiguous(), b["reward"][sl].t().contiguous(), b["done"][sl]))
+
+    def sample(self):
+        if not self.deque:
+            if len(self.store) <= self.cfg.BUFFER_SIZE:
+                return False
+            self.bufferSave(1)
+        return self.deque.pop(0)
+
+    def __len__(self):
+        return len(self.store)
+
+
+class Learner:
+    def __init__(self, cfg: ImpalaConfig | None = None, connect=None):
+        self.cfg = cfg or ImpalaConfig.from_configuration()
+        self.device = torch.device(self.cfg.LEARNER_DEVICE)
+        self.model = GraphAgent(self.cfg.MODEL).to(self.device)
+        self.mOptim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
+        self._connect = connect
+        self._memory = Replay(self.cfg, connect)
+        self.last = {}
+
+    def forward(self, state, action):
+        """IMPALA/Learner.py:70-83: pi(a|s) of the taken action and V(s)."""
+        out = self.model.forward([state])[0]
+        A = self.cfg.ACTION_SIZE
+        policy = torch.softmax(out[:, :A], dim=-1)
+        pi_a = policy.gather(1, action.view(-1, 1).long())[:, 0]
+        return pi_a, out[:, -1]
+
+    def train(self, transition, step=0):
+        c = self.cfg
+        T, B, A = c.UNROLL_STEP, c.BATCHSIZE, c.ACTION_SIZE
+        dev = self.device
+        state, action, mu, reward, done = [torch.as_tensor(x).to(dev) for x in transition]
+        with torch.no_grad():
+            s = state.float().div_(255.0).view(T + 1, B, 4, 84, 84)            # :131-140
+            last, seq = s[-1], s[:-1].reshape(-1, 4, 84, 84)
+            boot = (self.model.forward([last])[0][:, -1] * done.float().view(-1)).contiguous()   # :143
+            pi_a, value = self.forward(seq, action.reshape(-1))                 # :147
+            vt, adv = R.vtrace(pi_a.view(T, B).contiguous(), mu.float().view(T, B).contiguous(),
+                               value.view(T, B).contiguous(), boot, reward.float().view(T, B).contiguous(),
+                               c.GAMMA, c.C_LAMBDA, c.C_VALUE, c.P_VALUE)       # :151-215 in one launch
+        # calLoss (:95-119): second forward with grad
+        out = self.model.forward([seq])[0]
+        logp = torch.log_softmax(out[:, :A], dim=-1)
+        p = logp.exp()
+        entropy = -(p * logp).sum(-1, keepdim=True)
+        sel = logp.gather(1, action.reshape(-1, 1).long())
+        obj_actor = torch.mean(sel * adv.view(-1, 1) + c.ENTROPY_R * entropy)
+        critic = torch.mean((out[:, -1] - vt.view(-1)).pow(2)) / 2
+        self.mOptim.zero_grad(set_to_none=False)
+        (-obj_actor + critic).backward()                                         # :223-225
+        self.step(step)
+        self.last = {"objActor": obj_actor.detach(), "criticLoss": critic.detach(), "vtarget": vt, "advantage": adv}
+
+    def step(self, step=0):
+        """IMPALA/Learner.py:258-266: clip at 40, RMSprop."""
+        self.model.clippingNorm(40)
+        self.mOptim.step()
+
+    def state_dict(self):
+        return ({k: v.cpu() for k, v in self.model.state_dict().items()},)
+
+    def run(self, max_steps=None):
+        import time
+        while len(self._memory) <= self.cfg.BUFFER_SIZE:
+            time.sleep(0.05)
+        t = 0
+        while max_steps is None or t < max_steps:
+            tr = self._memory.sample()
+            if tr is False:
+                time.sleep(0.2)
+                continue
+            self.train(tr, t)
+            t += 1
+        return t

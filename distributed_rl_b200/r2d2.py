@@ -1,0 +1,191 @@
+"""R2D2 learner side with the reference's surface (R2D2/ReplayMemory.py:23-185,
+R2D2/Learner.py:39-339): sequences of FIXED_TRAJECTORY steps with a stored LSTM
+state live in HBM; burn-in, double-Q n-step targets with value rescaling, the
+mixed max/mean sequence priority and dLoss/dQ come from one kernel
+(b2rl_r2d2_target) instead of a D2H hop into NumPy fp64 (R2D2/Learner.py:145-181).
+
+SURVEY §8a-note 1: the shipped action slice `action[FIXED_TRAJECTORY-MEM:-1]`
+(:111) only runs when MEM == T/2; `[MEM:-1]` (what :120 uses for the rewards)
+is used here, identical whenever the reference runs at all.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import replay as R
+from .agent import GraphAgent
+from .apex import make_optimizer, _MemoryView
+
+
+def default_r2d2_model() -> dict:
+    """cfg/r2d2.json:33-103 (configuration values)."""
+    return {
+        "module00": {"netCat": "CNN2D", "iSize": 4, "nLayer": 4, "fSize": [8, 4, 3, -1], "nUnit": [32, 64, 64],
+                     "padding": [0, 0, 0], "stride": [4, 2, 1], "act": ["relu", "relu", "relu"],
+                     "BN": [False] * 4, "linear": True, "input": [0], "prior": 0},
+        "module01": {"netCat": "ViewV2", "prevNodeNames": ["module00"], "input": [1], "prior": 1},
+        "module02": {"netCat": "LSTMNET", "hiddenSize": 512, "nLayer": 1, "iSize": 3136, "device": "cpu",
+                     "FlattenMode": True, "return_hidden": False, "prior": 2, "prevNodeNames": ["module01"]},
+        "module03": {"netCat": "MLP", "iSize": 512, "nLayer": 2, "fSize": [512, 6], "act": ["relu", "linear"],
+                     "BN": [False] * 3, "prior": 3, "prevNodeNames": ["module02"]},
+        "module03_1": {"netCat": "MLP", "iSize": 512, "nLayer": 2, "fSize": [512, 1], "act": ["relu", "linear"],
+                       "BN": [False] * 3, "prior": 3, "prevNodeNames": ["module02"]},
+        "module04": {"netCat": "Add", "prior": 4, "prevNodeNames": ["module03", "module03_1"]},
+        "module04_1": {"netCat": "Mean", "prior": 4, "prevNodeNames": ["module03"]},
+        "module05": {"netCat": "Substract", "prior": 5, "prevNodeNames": ["module04", "module04_1"],
+                     "output": True},
+    }
+
+
+@dataclass
+class R2D2Config:
+    BATCHSIZE: int = 32
+    ACTION_SIZE: int = 6
+    ALPHA: float = 0.9
+    BETA: float = 0.4
+    GAMMA: float = 0.997
+    UNROLL_STEP: int = 5
+    FIXED_TRAJECTORY: int = 80
+    MEM: int = 20
+    USE_RESCALING: bool = True
+    REPLAY_MEMORY_LEN: int = 10000
+    BUFFER_SIZE: int = 1000
+    TARGET_FREQUENCY: int = 2500
+    LEARNER_DEVICE: str = "cuda:0"
+    REDIS_SERVER: str = "localhost"
+    OPTIM_INFO: dict = field(default_factory=lambda: {"name": "adam", "lr": 1e-4, "eps": 0.001})
+    MODEL: dict = field(default_factory=default_r2d2_model)
+
+    @staticmethod
+    def from_configuration():
+        import configuration as C
+        names = ("BATCHSIZE", "ACTION_SIZE", "ALPHA", "BETA", "GAMMA", "UNROLL_STEP", "FIXED_TRAJECTORY", "MEM",
+                 "USE_RESCALING", "REPLAY_MEMORY_LEN", "BUFFER_SIZE", "TARGET_FREQUENCY", "LEARNER_DEVICE",
+                 "REDIS_SERVER", "OPTIM_INFO", "MODEL")
+        return R2D2Config(**{k: getattr(C, k) for k in names})
+
+
+class Replay(threading.Thread):
+    """R2D2/ReplayMemory.py Replay: batch = [(h0, h1), s, a, r, notdone, w, idx] (:118-120)."""
+
+    def __init__(self, cfg: R2D2Config | None = None, connect=None):
+        super().__init__(daemon=True)
+        self.cfg = cfg or R2D2Config.from_configuration()
+        self.device = torch.device(self.cfg.LEARNER_DEVICE)
+        self.store = R.DeviceReplay(self.cfg.REPLAY_MEMORY_LEN, R.r2d2_fields(self.cfg.FIXED_TRAJECTORY),
+                                    self.device)
+        self.memory = _MemoryView(self.store, self.cfg.BETA)
+        self.connect, self.cond, self.lock = connect, False, False
+        self.deque, self.total_frame = [], 0
+
+    def push_arrays(self, s, a, r, h0, h1, notdone, p):
+        self.store.push([s, a, r, h0, h1, notdone], p)
+        self.total_frame += int(torch.as_tensor(p).numel())
+
+    def buffer(self, m: int = 1):
+        B = self.cfg.BATCHSIZE
+        idx, _, w = self.store.sample(B * m, beta=self.cfg.BETA)
+        b = self.store.gather(idx)
+        for k in range(m):
+            sl = slice(k * B, (k + 1) * B)
+            h0 = b["h0"][sl].unsqueeze(0).contiguous()     # (1, B, 512) like torch.cat(..., 1) at :87-88
+            h1 = b["h1"][sl].unsqueeze(0).contiguous()
+            self.deque.append([(h0, h1), b["state"][sl], b["action"][sl], b["reward"][sl], b["notdone"][sl],
+                               w[sl], idx[sl]])
+
+    def sample(self):
+        if not self.deque:
+            if len(self.store) <= self.cfg.BUFFER_SIZE:
+                return False
+            self.buffer(1)
+        return self.deque.pop(0)
+
+    def update(self, idx, vals):
+        if isinstance(idx, (list, tuple)):
+            idx = torch.stack([torch.as_tensor(i) for i in idx])
+        self.store.update(torch.as_tensor(idx).to(self.device), torch.as_tensor(vals).to(self.device))
+
+
+class Learner:
+    def __init__(self, cfg: R2D2Config | None = None, connect=None):
+        self.cfg = cfg or R2D2Config.from_configuration()
+        self.device = torch.device(self.cfg.LEARNER_DEVICE)
+        self.model = GraphAgent(self.cfg.MODEL).to(self.device)
+        self.target_model = GraphAgent(self.cfg.MODEL).to(self.device)
+        self.optim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
+        self.connect = connect
+        self.memory = Replay(self.cfg, connect)
+
+    def train(self, transition, t=0):
+        c = self.cfg
+        T, MEM, B, A = c.FIXED_TRAJECTORY, c.MEM, c.BATCHSIZE, c.ACTION_SIZE
+        L = T - MEM
+        (h0, h1), state, action, reward, notdone, weight, idx = transition
+        dev = self.device
+        weight = torch.as_tensor(weight).to(dev, torch.float32)
+        h0, h1 = h0.to(dev), h1.to(dev)
+        self.model.setCellState((h0, h1))                       # :86-87
+        self.target_model.setCellState((h0, h1))
+        state = torch.as_tensor(state).to(dev).float() / 255.0  # :89-90
+        sv = state.permute(1, 0, 2, 3, 4).contiguous()          # time-major, :93
+        burn = sv[:MEM].reshape(-1, 4, 84, 84)
+        window = sv[MEM:].reshape(-1, 4, 84, 84)
+        with torch.no_grad():                                   # burn-in, :99-104
+            shape = torch.tensor([MEM, B, -1])
+            self.model.forward([burn, shape])
+            self.target_model.forward([burn, shape])
+            self.model.detachCellState()
+            self.target_model.detachCellState()
+        shape = torch.tensor([L, B, -1])
+        q = self.model.forward([window, shape])[0].view(L, B, A)              # :121
+        with torch.no_grad():
+            q_target = self.target_model.forward([window, shape])[0].view(L, B, A)   # :132
+        act = torch.as_tensor(action).to(dev, torch.int64).t()[MEM:-1].contiguous()      # (L-1, B)
+        rew = torch.as_tensor(reward).to(dev, torch.float32).t()[MEM:-1].contiguous()
+        nd = torch.as_tensor(notdone).to(dev, torch.float32).contiguous()
+        out = R.r2d2_target(q.detach().contiguous(), q_target.contiguous(), act, rew, nd, weight,
+                            c.UNROLL_STEP, c.GAMMA, c.ALPHA, c.USE_RESCALING)
+        q.backward(out["grad_q"])                               # == loss.backward(), :189-192
+        info = self.step()
+        info["mean_value"] = out["scalars"][1]
+        info["loss"] = out["scalars"][0]
+        return info, out["prio"], idx
+
+    def step(self):
+        """R2D2/Learner.py:200-215: norm, clip at 40, Adam."""
+        params = self.model.getParameters()
+        grads = [p.grad for p in params if p.grad is not None]
+        p_norm = torch.stack(torch._foreach_norm(grads, 2)).sum().sqrt()
+        torch.nn.utils.clip_grad_norm_(params, 40, foreach=True)
+        self.optim.step()
+        self.optim.zero_grad(set_to_none=False)
+        return {"p_norm": p_norm}
+
+    @property
+    def state_dict(self):
+        return {k: v.cpu() for k, v in self.model.state_dict().items()}
+
+    @property
+    def target_state_dict(self):
+        return {k: v.cpu() for k, v in self.target_model.state_dict().items()}
+
+    def run(self, max_steps=None):
+        import time
+        while len(self.memory.memory) <= self.cfg.BUFFER_SIZE:
+            time.sleep(0.05)
+        step = 0
+        while max_steps is None or step < max_steps:
+            batch = self.memory.sample()
+            if batch is False:
+                time.sleep(0.002)
+                continue
+            info, prio, idx = self.train(batch)
+            self.memory.update(idx, prio)
+            step += 1
+            if step % self.cfg.TARGET_FREQUENCY == 0:
+                self.target_model.updateParameter(self.model, 1)
+        return step

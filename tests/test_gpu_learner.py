@@ -111,3 +111,103 @@ def test_fused_graph_step_equals_eager_step(apex):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=5e-5)  # cuDNN picks algos per call
     assert (te != tg).float().mean() < 0.01       # same slots updated with (nearly) the same priorities
     assert le == lg and le >= 5                   # sample + rng advance, gather, target, update
+
+
+def test_r2d2_learner_train_matches_oracle_and_autograd():
+    """R2D2 mirror: priorities == oracle on the captured Q tensors; the parameter update equals
+    loss.backward() of 0.5*mean(w*(y - q_sa)^2) (R2D2/Learner.py:184-192) + clip 40 + Adam."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import copy
+    from oracle import oracle as O
+    from distributed_rl_b200 import r2d2
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    T, MEM, B = 16, 8, 4
+    cfg = r2d2.R2D2Config(BATCHSIZE=B, FIXED_TRAJECTORY=T, MEM=MEM, REPLAY_MEMORY_LEN=64, BUFFER_SIZE=0)
+    torch.manual_seed(0)
+    L = r2d2.Learner(cfg)
+    with torch.no_grad():
+        for p in L.target_model.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    ref_model = copy.deepcopy(L.model)
+    ref_opt = r2d2.make_optimizer(cfg.OPTIM_INFO, ref_model.getParameters(), capturable=False)
+    rng = np.random.default_rng(0)
+    n = 64
+    L.memory.push_arrays(rng.integers(0, 256, size=(n, T, 4, 84, 84), dtype=np.uint8),
+                         rng.integers(0, 6, size=(n, T)).astype(np.int32),
+                         rng.standard_normal((n, T)).astype(np.float32),
+                         (rng.standard_normal((n, 512)) * 0.1).astype(np.float32),
+                         (rng.standard_normal((n, 512)) * 0.1).astype(np.float32),
+                         (rng.random(n) > 0.3).astype(np.float32), rng.uniform(0.1, 1, n).astype(np.float32))
+    batch = L.memory.sample()
+    (h0, h1), s, a, r, nd, w, idx = batch
+    cap = {}
+    om, ot = L.model.forward, L.target_model.forward
+
+    def fm(x):
+        o = om(x); cap.setdefault("q", []).append(o[0]); return o
+
+    def ft(x):
+        o = ot(x); cap.setdefault("qt", []).append(o[0]); return o
+
+    L.model.forward, L.target_model.forward = fm, ft
+    info, prio, idx2 = L.train(batch)
+    Lw = T - MEM
+    q = cap["q"][1].detach().view(Lw, B, 6).cpu().numpy()
+    qt = cap["qt"][1].detach().view(Lw, B, 6).cpu().numpy()
+    act = a.t()[MEM:-1].cpu().numpy(); rew = r.t()[MEM:-1].cpu().numpy()
+    tgt, td, oprio, gq, oinfo = O.r2d2_target(q, qt, act, rew, nd.cpu().numpy(), w.cpu().numpy(),
+                                              cfg.UNROLL_STEP, cfg.GAMMA, cfg.ALPHA, True)
+    np.testing.assert_allclose(prio.cpu().numpy(), oprio, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(float(info["mean_value"]), oinfo["mean_value"], atol=1e-6)
+    # autograd restatement on the copy
+    ref_model.setCellState((h0, h1))
+    sf = (s.float() / 255.).permute(1, 0, 2, 3, 4).contiguous()
+    with torch.no_grad():
+        ref_model.forward([sf[:MEM].reshape(-1, 4, 84, 84), torch.tensor([MEM, B, -1])])
+        ref_model.detachCellState()
+    qr = ref_model.forward([sf[MEM:].reshape(-1, 4, 84, 84), torch.tensor([Lw, B, -1])])[0].view(Lw, B, 6)
+    sel = qr[:-1].gather(2, a.t()[MEM:-1].long().unsqueeze(-1))[..., 0]
+    loss = torch.mean(w.view(1, -1) * (torch.from_numpy(tgt).cuda() - sel) ** 2) * 0.5
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(ref_model.getParameters(), 40)
+    ref_opt.step()
+    for p, pr in zip(L.model.parameters(), ref_model.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), pr.detach().cpu().numpy(), rtol=1e-4, atol=2e-6)
+    L.memory.update(list(idx2), prio)
+    np.testing.assert_allclose(L.memory.store.priorities()[idx2].cpu().numpy(), prio.cpu().numpy())
+
+
+def test_impala_learner_train_matches_oracle():
+    """IMPALA mirror: V-trace targets/advantages == oracle on the learner's own pi, V; params move."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import oracle as O
+    from distributed_rl_b200 import impala
+    torch.backends.cudnn.allow_tf32 = False
+    T, B, n = 20, 8, 32
+    cfg = impala.ImpalaConfig(BATCHSIZE=B, UNROLL_STEP=T, REPLAY_MEMORY_LEN=n, BUFFER_SIZE=0)
+    torch.manual_seed(1)
+    L = impala.Learner(cfg)
+    rng = np.random.default_rng(1)
+    L._memory.push_arrays(rng.integers(0, 256, size=(n, T + 1, 28224), dtype=np.uint8),
+                          rng.integers(0, 6, size=(n, T)).astype(np.int32),
+                          rng.uniform(0.05, 0.9, size=(n, T)).astype(np.float32),
+                          rng.standard_normal((n, T)).astype(np.float32),
+                          (rng.random(n) > 0.3).astype(np.float32))
+    tr = L._memory.sample()
+    s, a, mu, r, done = tr
+    assert s.shape == (T + 1, B, 28224) and a.shape == (T, B)
+    with torch.no_grad():
+        sf = (s.float() / 255.).view(T + 1, B, 4, 84, 84)
+        boot = L.model.forward([sf[-1]])[0][:, -1] * done
+        pi_a, v = L.forward(sf[:-1].reshape(-1, 4, 84, 84), a.reshape(-1))
+    before = [p.detach().clone() for p in L.model.parameters()]
+    L.train(tr, 0)
+    ovt, oadv, _ = O.vtrace(pi_a.view(T, B).cpu().numpy(), mu.cpu().numpy(), v.view(T, B).cpu().numpy(),
+                            boot.cpu().numpy(), r.cpu().numpy(), cfg.GAMMA, cfg.C_LAMBDA, cfg.C_VALUE, cfg.P_VALUE)
+    np.testing.assert_allclose(L.last["vtarget"].cpu().numpy(), ovt, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(L.last["advantage"].cpu().numpy(), oadv, rtol=1e-5, atol=1e-5)
+    assert any((b != p).any().item() for b, p in zip(before, L.model.parameters()))
+    assert all(torch.isfinite(p).all().item() for p in L.model.parameters())
