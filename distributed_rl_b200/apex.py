@@ -222,15 +222,10 @@ class Learner:
         """Replay-sharded data parallelism: every rank owns a replay shard and
         samples locally; per step one NCCL all-reduce (AVG) of the gradients, kept in ONE flat
         bucket so it is a single collective, and one MAX all-reduce of the max IS weight."""
-        import torch.distributed as dist
-        self._dist = dist
-        self._world = dist.get_world_size()
-        params = self.model.getParameters()
-        self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=self.device)
-        off = 0
-        for p in params:
-            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        from . import dist as D
+        self._D = D
+        self._world = D.world()
+        self._bucket = D.FlatGradBucket(self.model.getParameters(), self.device)
         self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)
 
     def build_model(self):
@@ -264,7 +259,7 @@ class Learner:
                             self.gamma_n, self.cfg.ALPHA)
         q.backward(out["grad_q"])                      # == loss.backward(), :112-115
         if self._world > 1:
-            self._dist.all_reduce(self._flat_grad, op=self._dist.ReduceOp.AVG)
+            self._bucket.all_reduce_mean()
         return out
 
     def train(self, transition, t=0):
@@ -303,8 +298,7 @@ class Learner:
         def body():
             max_w = None
             if self._world > 1:      # priority-max reduction: normalise IS weights by the global max
-                max_w = st.max_weight(self.cfg.BETA, out=self._max_w)
-                self._dist.all_reduce(max_w, op=self._dist.ReduceOp.MAX)
+                max_w = self._D.all_reduce_max_(st.max_weight(self.cfg.BETA, out=self._max_w))
             idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
             b = st.gather(idx)
             out = self._forward_backward(b["state"], b["action"].to(torch.int64), b["reward"],

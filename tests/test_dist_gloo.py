@@ -1,0 +1,94 @@
+"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: flat gradient
+bucket averaging, the priority-max reduction that makes sharded IS weights equal
+the single-replay formula, slot sharding, and bench.py's reference arm under
+torchrun (rank != 0 exits quietly)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, REPO)
+    from distributed_rl_b200 import dist as D
+    from oracle import oracle as O
+    out = {}
+    # 1. flat bucket: mean of per-rank gradients, grads stay views of the bucket
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(4, 3, bias=False), torch.nn.Linear(3, 2, bias=False))
+    bucket = D.FlatGradBucket(lin.parameters())
+    x = torch.full((5, 4), float(rank + 1))
+    lin(x).sum().backward()
+    local = bucket.flat.clone()
+    bucket.all_reduce_mean()
+    both = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(both, local)
+    out["bucket_ok"] = bool(torch.allclose(bucket.flat, sum(both) / world))
+    out["views_ok"] = all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())
+    # 2. priority-max reduction: shard-local IS weights / global max == single-replay formula
+    n, beta = 1024, 0.4
+    rng = np.random.default_rng(100 + rank)
+    p = ((np.abs(rng.standard_normal(n)).clip(max=1) + 1e-7) ** 0.6).astype(np.float32)
+    t = O.SumTreeOracle(n); t.build(p)
+    idx, _ = t.sample(rng.random(64))
+    w_local, prob, max_w_local = O.is_weights(p[idx], t.total, t.min_priority, n, beta)
+    mw = torch.tensor([float(max_w_local)])
+    D.all_reduce_max_(mw)
+    w_global = (w_local * (max_w_local / np.float32(mw.item()))).astype(np.float32)
+    # single-process statement of SURVEY §8e: P(i) = (1/G) p_i / S_g, N = G n, w = (N P)^-beta / max
+    shards = [torch.zeros(n) for _ in range(world)]
+    dist.all_gather(shards, torch.from_numpy(p))
+    NP = []
+    for sp in shards:
+        spn = sp.numpy().astype(np.float64)
+        NP.append((world * n) * (1.0 / world) * spn / spn.sum())
+    max_all = max(float((x ** -beta).max()) for x in NP)
+    expect = (NP[rank][idx] ** -beta) / max_all
+    out["isw_ok"] = bool(np.allclose(w_global, expect, rtol=2e-6))
+    out["mw"] = float(mw.item())
+    # 3. slot sharding covers [0, N) without overlap
+    rs = [D.shard_slots(1000, r, world) for r in range(world)]
+    out["shard_ok"] = sorted(i for r in rs for i in r) == list(range(1000))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_data_parallel_logic():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert res[r]["bucket_ok"] and res[r]["views_ok"] and res[r]["isw_ok"] and res[r]["shard_ok"], res[r]
+    assert res[0]["mw"] == res[1]["mw"]
+
+
+def test_bench_reference_arm_under_torchrun_only_rank0_prints(tmp_path):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29950 + os.getpid() % 40),
+           os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+           "--log2n", "12", "--batch", "8"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["cpu_baseline"]["kind"] == "port"
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["value"] > 0
