@@ -1,0 +1,70 @@
+"""Fused gather + conv_1 (tcgen05, kind::i8 with 4-digit weight split) against an fp64
+convolution of the same inputs (torch CPU).  Floating-point kernel -> tolerance, stated
+per assert; the contract is 1e-5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def R():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributed_rl_b200 import replay
+    return replay
+
+
+def _ref(frames_u8, w):
+    x = torch.from_numpy(frames_u8).double() / 255.0
+    return torch.nn.functional.conv2d(x, w.double().cpu(), stride=4)
+
+
+@pytest.mark.parametrize("n_nets,n,relu", [(1, 1, False), (1, 5, False), (2, 37, True), (2, 300, False), (1, 512, True)])
+def test_conv1_fused_matches_fp64_convolution(R, n_nets, n, relu):
+    rng = np.random.default_rng(n * 10 + n_nets)
+    rows = max(n, 8) + 11
+    frames = rng.integers(0, 256, size=(rows, 4, 84, 84), dtype=np.uint8)
+    frames[0, :, :8, :8] = 255                       # saturating corner
+    idx = rng.integers(0, rows, size=n)
+    idx[0] = 0
+    ws = [torch.empty(32, 4, 8, 8).uniform_(-0.0625, 0.0625, generator=torch.Generator().manual_seed(7 + i))
+          for i in range(n_nets)]
+    ws[0][3] = 0.0                                   # an all-zero output channel
+    ws[0][5, 0, 0, 0] = 0.9                          # one dominant weight: small digits of the others matter
+    pack = R.Conv1Pack(n_nets, "cuda:0")
+    for i, w in enumerate(ws):
+        pack.pack(i, w.cuda())
+    fr = torch.from_numpy(frames).cuda()
+    outs = R.conv1_fused(fr, torch.from_numpy(idx).cuda(), pack, relu=relu)
+    torch.cuda.synchronize()
+    for i, (o, w) in enumerate(zip(outs, ws)):
+        want = _ref(frames[idx], w)
+        if relu:
+            want = want.clamp_min(0)
+        got = o.cpu().double()
+        assert got.shape == want.shape == (n, 32, 20, 20)
+        err = (got - want).abs().max().item()
+        scale = want.abs().max().item()
+        assert err <= 2e-6 * max(scale, 1.0), (i, err, scale)     # ~fp32 rounding of a 256-term sum
+    # all rows in order when idx is None
+    outs2 = R.conv1_fused(fr[:n].contiguous(), None, pack, relu=False)
+    np.testing.assert_allclose(outs2[0].cpu().double().numpy(), _ref(frames[:n], ws[0]).numpy(), rtol=0, atol=2e-6 * 8)
+
+
+def test_conv1_fused_reads_replay_field_in_place(R):
+    """Gather fused: rows come straight from the DeviceReplay payload (no staging copy)."""
+    from oracle import oracle as O
+    cap = 256
+    rep = R.DeviceReplay(cap, fields=R.APEX_FIELDS)
+    rep.fill_hash(cap, seed=3)
+    rep.build(torch.rand(cap, device="cuda") + 0.1)
+    idx, _, _ = rep.sample(64)
+    w = torch.empty(32, 4, 8, 8).uniform_(-0.06, 0.06, generator=torch.Generator().manual_seed(1))
+    pack = R.Conv1Pack(1, "cuda:0"); pack.pack(0, w.cuda())
+    out = R.conv1_fused(rep.field_view("next_state"), idx, pack)[0]
+    frames = O.hash_rows(1, idx.cpu().numpy(), R.FRAME_STACK_BYTES, 3).reshape(-1, 4, 84, 84)
+    want = _ref(frames, w)
+    assert (out.cpu().double() - want).abs().max().item() <= 2e-6 * max(want.abs().max().item(), 1.0)
+    rep.close()
