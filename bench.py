@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="keep the network in NCHW (default: channels_last)")
+    ap.add_argument("--unfused-conv1", action="store_true", help="stage the batch and let cuDNN run conv_1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=6)
     return ap.parse_args()
@@ -189,7 +190,7 @@ def main():
 
     N, B = 1 << args.log2n, args.batch
     cfg = ApexConfig(BATCHSIZE=B, REPLAY_MEMORY_LEN=N, BUFFER_SIZE=0, LEARNER_DEVICE=str(dev),
-                     CHANNELS_LAST=not args.nchw)
+                     CHANNELS_LAST=not args.nchw, FUSED_CONV1=not args.unfused_conv1)
     torch.manual_seed(0)
     learner = Learner(cfg, connect=None, start_replay=False)
     if world > 1:   # identical initial weights on every rank
@@ -325,7 +326,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "clocks": clock_info,
-                "cuda_graph": use_graph, "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
+                "cuda_graph": use_graph, "fused_gather_conv1": bool(cfg.FUSED_CONV1), "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:

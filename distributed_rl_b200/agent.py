@@ -54,6 +54,23 @@ class ConvStack(nn.Sequential):
             x = layer(x)
         return x
 
+    def is_atari_conv1(self) -> bool:
+        """True if the first layer is the 8x8/stride-4, 4->32, bias-free conv followed by ReLU that
+        libb2rl's fused gather+conv1 kernel implements (cfg/ape_x.json, cfg/r2d2.json)."""
+        layers = list(self.children())
+        if len(layers) < 2 or not isinstance(layers[0], nn.Conv2d) or not isinstance(layers[1], nn.ReLU):
+            return False
+        c = layers[0]
+        return (c.in_channels, c.out_channels, c.kernel_size, c.stride, c.padding, c.bias) == \
+            (4, 32, (8, 8), (4, 4), (0, 0), None)
+
+    def forward_tail(self, y, relu_applied: bool):
+        """Continue after conv_1: `y` is conv_1's output (pre- or post-ReLU)."""
+        x = y
+        for layer in list(self.children())[2 if relu_applied else 1:]:
+            x = layer(x)
+        return x
+
 
 class DenseStack(nn.Sequential):
     """netCat MLP: Linear layers (bias off unless cfg says so) with activations."""
@@ -164,12 +181,29 @@ class GraphAgent(nn.Module):
                 self._recurrent.append(name)
 
     # -- execution: external inputs first, then upstream outputs (reference order) --
-    def forward(self, inputs):
-        vals = {}
+    def forward(self, inputs, preset: dict | None = None):
+        """`preset` maps node names to already-computed outputs (used by the fused conv_1 path)."""
+        vals = dict(preset) if preset else {}
         for name in self._order:
+            if name in vals:
+                continue
             srcs = [inputs[i] for i in self._ext[name]] + [vals[p] for p in self._prev[name]]
             vals[name] = getattr(self, name)(tuple(srcs))
         return tuple(vals[n] for n in self._outputs)
+
+    def first_conv_node(self):
+        """Name of the CNN2D node fed by external input 0, if it starts with the Atari conv_1."""
+        for name in self._order:
+            m = getattr(self, name)
+            if isinstance(m, ConvStack) and self._ext[name] == [0] and not self._prev[name]:
+                return name if m.is_atari_conv1() else None
+        return None
+
+    def forward_from_conv1(self, y, relu_applied: bool, extra_inputs=()):
+        """Forward pass given conv_1's output of the first CNN2D node (fused gather+conv1 kernel)."""
+        name = self.first_conv_node()
+        feat = getattr(self, name).forward_tail(y, relu_applied)
+        return self.forward([None, *extra_inputs], preset={name: feat})
 
     # -- the surface the learners call --------------------------------------------
     def getParameters(self):

@@ -50,6 +50,7 @@ class ApexConfig:
         "centered": True})
     MODEL: dict = field(default_factory=lambda: default_apex_model())
     CHANNELS_LAST: bool = True      # NHWC activations/weights: cuDNN's TF32 kernels skip their layout transposes
+    FUSED_CONV1: bool = True        # gather + conv_1 on the tcgen05 tensor cores (csrc/conv1.cu) in fused_step
 
     @staticmethod
     def from_configuration():
@@ -199,6 +200,26 @@ class Replay(threading.Thread):
         return None
 
 
+class _Conv1Gathered(torch.autograd.Function):
+    """conv_1 over replay rows `idx` of the `state` field.  Forward: fused gather+conv (tensor
+    cores, no staging).  Backward: only dL/dW is needed (the input is data); it is computed by
+    cuDNN from a gathered copy of the same rows — the one place the sampled s is staged."""
+
+    @staticmethod
+    def forward(ctx, weight, store, idx, pack, mem_format):
+        ctx.store, ctx.mem_format, ctx.wshape = store, mem_format, weight.shape
+        ctx.save_for_backward(idx)
+        return R.conv1_fused(store.field_view("state"), idx, pack, relu=False)[0]
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        x = ctx.store.gather(idx, ctx.store.alloc_batch(idx.numel(), ("state",)))["state"]
+        xf = (x.to(torch.float32) / 255.0).contiguous(memory_format=ctx.mem_format)
+        gw = torch.nn.grad.conv2d_weight(xf, ctx.wshape, gy, stride=4)
+        return gw, None, None, None, None
+
+
 class Learner:
     """APE_X/Learner.py Learner (:20-272): train / step / run / state_dict."""
 
@@ -285,6 +306,39 @@ class Learner:
         self.optim.zero_grad(set_to_none=False)
         return {"p_norm": p_norm}
 
+    # -- fused gather + conv_1 path ------------------------------------------------------------
+    def _conv1_ready(self) -> bool:
+        if not self.cfg.FUSED_CONV1 or self.model.first_conv_node() is None:
+            return False
+        if not hasattr(self, "_pack2"):
+            self._pack1 = R.Conv1Pack(1, self.device)     # online net (grad pass on s)
+            self._pack2 = R.Conv1Pack(2, self.device)     # online + target in one pass over s'
+            self._conv_name = self.model.first_conv_node()
+        return True
+
+    def _forward_backward_fused(self, idx, action, reward, done, weight):
+        """Same maths as _forward_backward, but s and s' are never staged as uint8/fp32 batches:
+        conv_1 reads the sampled rows straight from the replay payload (b2rl_conv1_fused)."""
+        st = self.memory.store
+        w_on = getattr(self.model, self._conv_name).conv_1.weight
+        w_tg = getattr(self.target_model, self._conv_name).conv_1.weight
+        self._pack1.pack(0, w_on)
+        self._pack2.pack(0, w_on)
+        self._pack2.pack(1, w_tg)
+        with torch.no_grad():
+            y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
+            qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
+            qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
+        y = _Conv1Gathered.apply(w_on, st, idx, self._pack1, self._mf)
+        q = self.model.forward_from_conv1(y, False)[0]                       # :78
+        notdone = 1.0 - done.to(torch.float32)
+        out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
+                            self.gamma_n, self.cfg.ALPHA)
+        q.backward(out["grad_q"])
+        if self._world > 1:
+            self._bucket.all_reduce_mean()
+        return out
+
     # -- the whole hot loop iteration as one CUDA graph -----------------------------------
     def fused_step(self, use_graph: bool = True):
         """sample -> gather -> forwards -> target -> backward -> RMSprop -> priority
@@ -294,15 +348,22 @@ class Learner:
             return self._static
         B = self.cfg.BATCHSIZE
         st = self.memory.store
+        fused_conv1 = self._conv1_ready()
 
         def body():
             max_w = None
             if self._world > 1:      # priority-max reduction: normalise IS weights by the global max
                 max_w = self._D.all_reduce_max_(st.max_weight(self.cfg.BETA, out=self._max_w))
             idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
-            b = st.gather(idx)
-            out = self._forward_backward(b["state"], b["action"].to(torch.int64), b["reward"],
-                                         b["next_state"], b["done"], w)
+            if fused_conv1:
+                if not hasattr(self, "_small"):
+                    self._small = st.alloc_batch(B, ("action", "reward", "done"))
+                b = st.gather(idx, self._small)        # scalar fields only; frames go through conv1_fused
+                out = self._forward_backward_fused(idx, b["action"].to(torch.int64), b["reward"], b["done"], w)
+            else:
+                b = st.gather(idx)
+                out = self._forward_backward(b["state"], b["action"].to(torch.int64), b["reward"],
+                                             b["next_state"], b["done"], w)
             info = self.step()
             st.update(idx, out["prio"])
             return {"scalars": out["scalars"], "p_norm": info["p_norm"], "prio": out["prio"], "idx": idx}

@@ -211,3 +211,28 @@ def test_impala_learner_train_matches_oracle():
     np.testing.assert_allclose(L.last["advantage"].cpu().numpy(), oadv, rtol=1e-5, atol=1e-5)
     assert any((b != p).any().item() for b, p in zip(before, L.model.parameters()))
     assert all(torch.isfinite(p).all().item() for p in L.model.parameters())
+
+
+def test_fused_conv1_step_equals_staged_step(apex):
+    """fused_step with the tcgen05 gather+conv_1 path == fused_step that stages the batch and lets
+    cuDNN run conv_1 (fp32, TF32 off): same sampled slots, same weights/priorities to fp32 noise."""
+    res = []
+    for fused in (False, True):
+        cfg = apex.ApexConfig(BATCHSIZE=64, REPLAY_MEMORY_LEN=8192, BUFFER_SIZE=0, LEARNER_DEVICE="cuda:0",
+                              FUSED_CONV1=fused)
+        torch.manual_seed(11)
+        L = apex.Learner(cfg, connect=None, start_replay=False)
+        with torch.no_grad():
+            for p in L.target_model.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+        _fill(L, 8192, seed=5)
+        outs = [L.fused_step(use_graph=False) for _ in range(3)]
+        torch.cuda.synchronize()
+        res.append(([p.detach().clone() for p in L.model.parameters()], L.memory.store.priorities().clone(),
+                    outs[-1]["idx"].clone(), outs[-1]["scalars"].clone()))
+    (p0, t0, i0, s0), (p1, t1, i1, s1) = res
+    assert torch.equal(i0, i1)                                   # same device RNG stream, same tree
+    np.testing.assert_allclose(s0.cpu().numpy(), s1.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(t0.cpu().numpy(), t1.cpu().numpy(), rtol=1e-3, atol=1e-5)
+    for a, b in zip(p0, p1):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=2e-5)

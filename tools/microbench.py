@@ -67,6 +67,21 @@ def main():
     nd = torch.ones(B, device=dev); w = torch.rand(B, device=dev)
     out = R.apex_target(*q, a, r, nd, w, 0.97, 0.6)
     res["apex_target_512_us"] = graph_time([lambda: R.apex_target(*q, a, r, nd, w, 0.97, 0.6, out=out)] * 10)
+    if args.payload:
+        wt = torch.empty(32, 4, 8, 8, device=dev).uniform_(-0.06, 0.06)
+        for nn_ in (1, 2):
+            pack = R.Conv1Pack(nn_, dev)
+            for i in range(nn_):
+                pack.pack(i, wt)
+            field = rep.field_view("next_state")
+            for n in (512, 4096):
+                idxs = [rep.sample(n)[0] for _ in range(6)]
+                out = torch.empty((nn_, n, 20, 20, 32), device=dev)
+                t = graph_time([(lambda ix=ix: R.conv1_fused(field, ix, pack, relu=True, out=out)) for ix in idxs])
+                res[f"conv1_fused_{nn_}net_{n}_us"] = t
+                res[f"conv1_fused_{nn_}net_{n}_frames_GBs"] = 28224 * n / t / 1e3
+                res[f"conv1_fused_{nn_}net_{n}_TOPS_i8"] = 2.0 * 512 * (128 * nn_) * 256 * n / t / 1e6
+        res["conv1_pack_us"] = graph_time([lambda: pack.pack(0, wt)] * 10)
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open(f"gpurun_out/microbench{args.tag}.json", "w"), indent=1)
