@@ -185,6 +185,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
