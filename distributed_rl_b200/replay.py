@@ -337,7 +337,7 @@ class Conv1Pack:
         assert n_nets in (1, 2)
         self.n_nets = n_nets
         self.device = torch.device(device)
-        self.bq = torch.empty(3 * n_nets * 32 * 256, dtype=torch.bfloat16, device=self.device)
+        self.bq = torch.empty(n_nets * 128 * 256, dtype=torch.int8, device=self.device)
         self.scale = torch.empty(n_nets * 32, dtype=torch.float32, device=self.device)
 
     def pack(self, net: int, weight: torch.Tensor) -> None:

@@ -194,16 +194,15 @@ int b2rl_vtrace(const float* pi_a_dev, const float* mu_a_dev, const float* value
  * (8x8, stride 4, 4 -> 32 channels, no bias; baseline/baseNetwork.py:165-172) applied to
  * frames[idx[k]] / 255 (APE_X/Learner.py:61-67,78,85,87) on the tcgen05 tensor cores, for one or
  * two networks (online + target) in one pass; the sampled uint8 frames are never staged in HBM.
- *   b2rl_conv1_pack   w_dev fp32 [32][4][8][8] of network `net` -> three bf16 terms (hi+mid+lo)
- *                     in the tensor-core operand layout (bq_out: 3*n_nets*32*256*2 bytes) and
- *                     the per-channel output scale 1/255 (scale_out: n_nets*32 fp32)
+ *   b2rl_conv1_pack   w_dev fp32 [32][4][8][8] of network `net` -> packed int8 digits
+ *                     (bq_out: n_nets*128*256 bytes) and per-channel scale (scale_out: n_nets*32 fp32)
  *   b2rl_conv1_fused  frames_dev: rows of 28 224 bytes (e.g. b2rl_replay_field_ptr of the state
  *                     field), idx_dev int64[n] or NULL (rows 0..n-1), out_dev fp32
  *                     [n_nets][n][20][20][32] (NHWC), relu != 0 applies ReLU. */
-int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, void* bq_out_dev,
+int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, int8_t* bq_out_dev,
                     float* scale_out_dev, void* stream);
 int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
-                     const void* bq_dev, const float* scale_dev, int32_t n_nets, float* out_dev,
+                     const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, float* out_dev,
                      int32_t relu, void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py's
