@@ -239,39 +239,67 @@ def main():
     value = B * world * args.steps / (ms / 1e3)
     scal = out["scalars"].tolist()
 
-    # ---- dominant hand-written kernel: the TMA gather, timed alone with CUDA events -------
+    # ---- dominant hand-written kernels, each timed alone with CUDA events (graph of `reps`
+    #      launches on distinct index sets -> no Python launch overhead, no L2 reuse of the rows) ----
     reps = 20
     idxs = [store.sample(B, beta=cfg.BETA, want_prob=False)[0] for _ in range(reps)]
-    outb = store.alloc_batch(B)
-    for i in range(3):
-        store.gather(idxs[i], outb)
-    torch.cuda.synchronize()
-    gg = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(gg):
-        for i in range(reps):
-            store.gather(idxs[i], outb)     # big-row bulk kernel + one small kernel per scalar field
-    gg.replay(); torch.cuda.synchronize()
-    g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-    g0.record(); gg.replay(); g1.record(); torch.cuda.synchronize()
-    gather_us = g0.elapsed_time(g1) * 1e3 / reps
-    # subtract nothing: the 3 small-field kernels are part of the gather of one transition
+
+    def time_graph(fn):
+        for i in range(3):
+            fn(idxs[i])
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(reps):
+                fn(idxs[i])
+        gr.replay(); torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(); gr.replay(); t1.record(); torch.cuda.synchronize()
+        del gr
+        return t0.elapsed_time(t1) * 1e3 / reps
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = ALG_BYTES_PER_TRANSITION_GATHER * B / (gather_us * 1e-6) / 1e9
-    roofline = {"kernel": "k_gather_bulk (+3 k_gather_small) — TMA bulk gather of one batch", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)" if peaks else "fallback 6650",
-                "traffic": None, "launch_us": gather_us, "algorithmic_bytes_per_launch": ALG_BYTES_PER_TRANSITION_GATHER * B,
-                "note": "a gather is a copy: HBM traffic = 2x the algorithmic (read-only) bytes, so frac <= 0.5 "
-                        "until the gather is fused into its consumer"}
-    prof = os.path.join(REPO, "profiles", "r01_gather_traffic.json")
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)" if peaks else "fallback 6650"
+    outb = store.alloc_batch(B)
+    gather_us = time_graph(lambda ix: store.gather(ix, outb))
+    g_ach = ALG_BYTES_PER_TRANSITION_GATHER * B / (gather_us * 1e-6) / 1e9
+    kernels = {"k_gather_bulk": {"launch_us": gather_us, "algorithmic_bytes_per_launch": ALG_BYTES_PER_TRANSITION_GATHER * B,
+                                 "achieved_GBs": g_ach, "frac": g_ach / peak,
+                                 "note": "whole minibatch (s, s', a, r, done) staged in one launch; a copy moves 2x its "
+                                         "algorithmic read bytes, so frac <= 0.5 for an unfused gather"}}
+    roofline = {"kernel": "k_gather_bulk — TMA bulk gather of one minibatch", "bound": "hbm", "achieved": g_ach,
+                "peak": peak, "unit": "GB/s", "frac": g_ach / peak, "peak_source": peak_src, "traffic": None,
+                "launch_us": gather_us, "algorithmic_bytes_per_launch": ALG_BYTES_PER_TRANSITION_GATHER * B}
+    if cfg.FUSED_CONV1 and learner._conv1_ready():
+        # fused gather + conv_1 for online+target nets over s': reads B frame stacks, writes 2 x B x (20,20,32) fp32
+        alg = B * (28224 + 2 * 400 * 32 * 4)
+        out2 = torch.empty((2, B, 20, 20, 32), device=dev)
+        nsf = store.field_view("next_state")
+        c_us = time_graph(lambda ix: R.conv1_fused(nsf, ix, learner._pack2, relu=True, out=out2))
+        c_ach = alg / (c_us * 1e-6) / 1e9
+        ops = 2.0 * (B * 400) * 256 * 256        # useful MACs x2 incl. the 4 weight digits (N=256 columns)
+        kernels["k_conv1_fused<2>"] = {"launch_us": c_us, "algorithmic_bytes_per_launch": alg, "achieved_GBs": c_ach,
+                                       "frac": c_ach / peak, "int8_TOPS": ops / (c_us * 1e-6) / 1e12,
+                                       "note": "reads 28 224 B per sampled s' directly from the replay payload "
+                                               "(no staging copy) and writes conv_1 activations of both networks"}
+        roofline = {"kernel": "k_conv1_fused<2> — fused TMA gather + im2col + tcgen05 conv_1 (online+target) of s'",
+                    "bound": "hbm", "achieved": c_ach, "peak": peak, "unit": "GB/s", "frac": c_ach / peak,
+                    "peak_source": peak_src, "traffic": None, "launch_us": c_us, "algorithmic_bytes_per_launch": alg,
+                    "note": "algorithmic bytes = sampled frames read (SURVEY §8d: 28 224 B per frame stack) + the two "
+                            "fp32 NHWC activation maps written; currently epilogue/issue-bound, not HBM-bound "
+                            "(tensor pipe 21.6 % active, profiles/r01_conv1.md)"}
+    roofline["kernels"] = kernels
+    prof = os.path.join(REPO, "profiles", "r01_traffic.json")
     if os.path.isfile(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            tr = json.load(open(prof))
+            key = "k_conv1_fused<2>" if "k_conv1_fused<2>" in kernels else "k_gather_bulk"
+            roofline["traffic"] = tr.get(key)
         except Exception:
             pass
 
@@ -334,7 +362,6 @@ def main():
         # CUDA graphs that hold NCCL kernels make destroy_process_group()/interpreter teardown hang:
         # drop them, drain the device, leave together, and exit without running destructors.
         learner._graph = None
-        del gg
         torch.cuda.synchronize()
         dist.barrier()
         os._exit(0)
