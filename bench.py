@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="keep the network in NCHW (default: channels_last)")
     ap.add_argument("--unfused-conv1", action="store_true", help="stage the batch and let cuDNN run conv_1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -107,12 +107,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------- #
 # reference arm / cpu baseline                                                  #
 # --------------------------------------------------------------------------- #
-def run_cpu_port(n_slots, batch, steps, warmup):
+def run_cpu_port(n_slots, batch, steps, warmup, threads=None):
     """`steps` train steps of the CPU port, sampled/assembled `m` at a time like the reference."""
     import torch
     from oracle.cpu_learner import CpuApexLearner
 
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     m = max(1, min(16, steps))
     L = CpuApexLearner(n_slots, batch, m=m, pool=2048, threads=cores)
@@ -129,14 +129,29 @@ def run_cpu_port(n_slots, batch, steps, warmup):
             "cycles": cycles, "parts": {k: v / cycles for k, v in parts.items()}}
 
 
+def best_cpu_port(n_slots, batch, steps, warmup):
+    """The reference leaves torch's intra-op thread count at its default (= all cores).  On a
+    many-core host that oversubscribes the small convolutions badly, so the port is timed at a few
+    thread counts and the FASTEST one is reported (with the count it used)."""
+    ncpu = os.cpu_count() or 1
+    best, tried = None, {}
+    for th in sorted({min(8, ncpu), min(32, ncpu), ncpu}):
+        r = run_cpu_port(n_slots, batch, steps, warmup, threads=th)
+        tried[th] = round(r["value"], 1)
+        if best is None or r["value"] > best["value"]:
+            best = r
+    best["tried_threads"] = tried
+    return best
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = 1 << args.log2n
-    steps = min(args.steps, 16)          # bounded sample: <= 16 train steps of 512 on the host cores
-    warm = min(args.warmup, 2)
-    r = run_cpu_port(n, args.batch, steps, warm)
+    steps = min(args.steps, 4)           # bounded sample: <= 4 train steps of 512 per thread setting
+    warm = min(args.warmup, 1)
+    r = best_cpu_port(n, args.batch, steps, warm)
     sample = (f"{r['cycles']} cycle(s) of {r['m']} train steps x batch {args.batch} at N=2^{args.log2n} "
               f"priorities (payload pool of 2048 pickled records), after {warm} warm-up step(s)")
     line = {
@@ -145,7 +160,8 @@ def reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
-                         "parts_s_per_cycle": r["parts"]},
+                         "parts_s_per_cycle": r["parts"], "tried_threads_tr_per_s": r["tried_threads"],
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -343,8 +359,9 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = run_cpu_port(N, B, args.cpu_steps, 1)
+        r = best_cpu_port(N, B, args.cpu_steps, 1)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "tried_threads_tr_per_s": r["tried_threads"], "host_cpus": os.cpu_count(),
                "sample": f"{r['cycles']} cycle(s) x {r['m']} train steps x batch {B} at N=2^{args.log2n} priorities "
                          f"(pool of 2048 pickled records), {r['seconds']:.1f} s of CPU work",
                "parts_s_per_cycle": r["parts"]}
