@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="keep the network in NCHW (default: channels_last)")
     ap.add_argument("--unfused-conv1", action="store_true", help="stage the batch and let cuDNN run conv_1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=48)
     return ap.parse_args()
 
 
@@ -131,15 +131,15 @@ def run_cpu_port(n_slots, batch, steps, warmup, threads=None):
 
 def best_cpu_port(n_slots, batch, steps, warmup):
     """The reference leaves torch's intra-op thread count at its default (= all cores).  On a
-    many-core host that oversubscribes the small convolutions badly, so the port is timed at a few
-    thread counts and the FASTEST one is reported (with the count it used)."""
+    many-core host that oversubscribes the small convolutions badly (measured: 64 tr/s at 128
+    threads vs 3200 tr/s at 32), so a 2-step probe picks the fastest of a few thread counts and the
+    bounded sample is then timed at that count (reported as `cores`)."""
     ncpu = os.cpu_count() or 1
-    best, tried = None, {}
+    tried = {}
     for th in sorted({min(8, ncpu), min(32, ncpu), ncpu}):
-        r = run_cpu_port(n_slots, batch, steps, warmup, threads=th)
-        tried[th] = round(r["value"], 1)
-        if best is None or r["value"] > best["value"]:
-            best = r
+        tried[th] = round(run_cpu_port(n_slots, batch, 2, 1, threads=th)["value"], 1)
+    best_th = max(tried, key=tried.get)
+    best = run_cpu_port(n_slots, batch, steps, warmup, threads=best_th)
     best["tried_threads"] = tried
     return best
 
@@ -149,7 +149,7 @@ def reference_arm(args):
     if rank != 0:
         return
     n = 1 << args.log2n
-    steps = min(args.steps, 4)           # bounded sample: <= 4 train steps of 512 per thread setting
+    steps = max(1, min(args.steps, 48))  # bounded sample: <= 48 train steps of 512 (about 10 s of CPU work)
     warm = min(args.warmup, 1)
     r = best_cpu_port(n, args.batch, steps, warm)
     sample = (f"{r['cycles']} cycle(s) of {r['m']} train steps x batch {args.batch} at N=2^{args.log2n} "
