@@ -152,6 +152,18 @@ class Replay(threading.Thread):
             self.store.push([s, ns, a, r, d], p)
         self.total_frame += int(torch.as_tensor(p).numel())
 
+    def begin_ingest(self, s, ns, a, r, d) -> None:
+        """Pipelined ingest, phase 1: retire the slots about to be overwritten and start the
+        host->device copy on the ingest stream (overlaps the learner step in flight)."""
+        with self._lock:
+            self.store.push_begin([s, ns, a, r, d], int(torch.as_tensor(a).numel()))
+
+    def commit_ingest(self, p) -> None:
+        """Phase 2: wait for the copy, publish the new priorities (records become sampleable)."""
+        with self._lock:
+            self.store.push_commit(p)
+        self.total_frame += int(torch.as_tensor(p).numel())
+
     def run(self):
         """Poll the actors' Redis list like APE_X/ReplayMemory.py:118-161."""
         if self.connect is None:

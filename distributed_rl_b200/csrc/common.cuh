@@ -114,4 +114,5 @@ struct b2rl_replay {
   uint64_t* rng_dev = nullptr;     // [2] device-resident Philox stream {seed, counter}
   int64_t size = 0;       // valid slots
   int64_t head = 0;       // next slot to write
+  int64_t reserved = 0;   // slots zeroed by b2rl_replay_reserve and not yet committed
 };

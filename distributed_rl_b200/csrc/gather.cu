@@ -424,6 +424,52 @@ extern "C" int b2rl_replay_push(b2rl_replay* h, const void* const* fields_src, c
   return B2RL_OK;
 }
 
+extern "C" int b2rl_replay_reserve(b2rl_replay* h, int64_t n, int64_t* start_slot, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(n >= 1 && n <= h->capacity, "n out of range (1..capacity)");
+  B2RL_REQUIRE(h->reserved == 0, "a reservation is already pending (call b2rl_replay_commit first)");
+  DeviceGuard g(h->device);
+  int rc = b2rl_tree_update_impl(h, nullptr, h->head, nullptr, 0.0f, n, (cudaStream_t)stream);
+  if (rc != B2RL_OK) return rc;
+  const int64_t overwritten = h->size + n - h->capacity;     // records that just became unsampleable
+  if (overwritten > 0) h->size -= overwritten;
+  h->reserved = n;
+  if (start_slot) *start_slot = h->head;
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_copy_payload(b2rl_replay* h, const void* const* fields_src, int64_t start_slot,
+                                        int64_t n, void* stream) {
+  B2RL_REQUIRE(h != nullptr && fields_src != nullptr, "null argument");
+  B2RL_REQUIRE(n >= 1 && n <= h->capacity && start_slot >= 0 && start_slot < h->capacity, "range out of bounds");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t first = (start_slot + n <= h->capacity) ? n : (h->capacity - start_slot);
+  for (int f = 0; f < h->n_fields; ++f) {
+    const uint8_t* src = (const uint8_t*)fields_src[f];
+    if (src == nullptr) continue;
+    const int64_t rb = h->field_bytes[f];
+    B2RL_CUDA(cudaMemcpyAsync(h->field[f] + start_slot * rb, src, (size_t)(first * rb), cudaMemcpyDefault, st));
+    if (first < n)
+      B2RL_CUDA(cudaMemcpyAsync(h->field[f], src + first * rb, (size_t)((n - first) * rb), cudaMemcpyDefault, st));
+  }
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_replay_commit(b2rl_replay* h, const float* prios, int64_t n, void* stream) {
+  B2RL_REQUIRE(h != nullptr && prios != nullptr, "null argument");
+  B2RL_REQUIRE(n >= 1 && n == h->reserved, "commit size must equal the pending reservation");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  B2RL_CUDA(cudaMemcpyAsync(h->scratch_val, prios, (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+  int rc = b2rl_tree_update_impl(h, nullptr, h->head, h->scratch_val, 0.0f, n, st);
+  if (rc != B2RL_OK) return rc;
+  h->head = (h->head + n) % h->capacity;
+  h->size = (h->size + n > h->capacity) ? h->capacity : h->size + n;
+  h->reserved = 0;
+  return B2RL_OK;
+}
+
 extern "C" int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream) {
   B2RL_REQUIRE(h != nullptr, "null handle");
   B2RL_REQUIRE(delta >= 0 && delta <= h->size, "delta out of range (0..size)");

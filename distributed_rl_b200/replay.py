@@ -177,6 +177,43 @@ class DeviceReplay:
         else:
             self._inflight = keep
 
+    # -- pipelined ingest: H2D of the next batch overlaps the current learner step ------------
+    def push_begin(self, fields: Sequence, n: int) -> None:
+        """reserve (current stream) + payload copy on a private ingest stream.  Pair with push_commit."""
+        if not hasattr(self, "_ingest_stream"):
+            self._ingest_stream = torch.cuda.Stream(self.device)
+            self._ev_reserved = torch.cuda.Event()
+            self._ev_copied = torch.cuda.Event()
+        start = C.c_int64()
+        check(self.lib.b2rl_replay_reserve(self._h, int(n), C.byref(start), self._st()))
+        self._ev_reserved.record(torch.cuda.current_stream(self.device))
+        keep = []
+        ptrs = (C.c_void_p * _lib.MAX_FIELDS)()
+        for i, (f, x) in enumerate(zip(self.fields, fields)):
+            if x is None:
+                ptrs[i] = None
+                continue
+            t = torch.as_tensor(x)
+            assert t.dtype == f.dtype and t.is_contiguous() and t.numel() * t.element_size() == n * f.nbytes
+            keep.append(t)
+            ptrs[i] = t.data_ptr()
+        with torch.cuda.stream(self._ingest_stream):
+            self._ingest_stream.wait_event(self._ev_reserved)
+            check(self.lib.b2rl_replay_copy_payload(self._h, ptrs, start.value, int(n),
+                                                    self._ingest_stream.cuda_stream))
+            self._ev_copied.record(self._ingest_stream)
+        self._pending = (keep, int(n))
+
+    def push_commit(self, priorities) -> None:
+        """Make the records copied by push_begin sampleable (current stream waits for the copy)."""
+        keep, n = self._pending
+        pr = torch.as_tensor(priorities).to(torch.float32).contiguous()
+        assert pr.numel() == n
+        torch.cuda.current_stream(self.device).wait_event(self._ev_copied)
+        check(self.lib.b2rl_replay_commit(self._h, pr.data_ptr(), n, self._st()))
+        self._inflight = keep + [pr]
+        self._pending = None
+
     def evict(self, delta: int) -> None:
         check(self.lib.b2rl_replay_evict(self._h, int(delta), self._st()))
 

@@ -77,6 +77,18 @@ int b2rl_replay_field_ptr(const b2rl_replay* h, int32_t field, void** ptr_dev);
 int b2rl_replay_push(b2rl_replay* h, const void* const* fields_src, const float* prios,
                      int64_t n, void* stream);
 
+/* Pipelined ingest — the same PER.push, split so that the host->device copy of the NEXT batch of
+ * records can run on its own stream while the learner step of the current batch computes:
+ *   reserve   (learner stream) priorities of the next n ring slots := 0, so the records about to
+ *             be overwritten can no longer be sampled; *start_slot receives the first slot
+ *   copy      (ingest stream, after an event recorded behind `reserve`) payload rows only
+ *   commit    (learner stream, after the copy's event) priorities + root paths; advances the ring
+ * reserve/commit must alternate; n <= capacity. */
+int b2rl_replay_reserve(b2rl_replay* h, int64_t n, int64_t* start_slot, void* stream);
+int b2rl_replay_copy_payload(b2rl_replay* h, const void* const* fields_src, int64_t start_slot, int64_t n,
+                             void* stream);
+int b2rl_replay_commit(b2rl_replay* h, const float* prios, int64_t n, void* stream);
+
 /* PER.remove_to_fit (baseline/PER.py:118-127): drop the `delta` oldest
  * records (priority := 0 so they can never be sampled; size -= delta). */
 int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream);

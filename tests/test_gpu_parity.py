@@ -156,6 +156,34 @@ def test_ring_push_evict_matches_model(R):
     rep.close()
 
 
+def test_pipelined_ingest_matches_ring_model(R):
+    """reserve / copy (ingest stream) / commit == PER.push on the ring; reserved slots are unsampleable."""
+    cap, n = 512, 96
+    rng = np.random.default_rng(8)
+    fields = (R.Field("x", torch.uint8, (64,)), R.Field("a", torch.int32, ()))
+    rep = R.DeviceReplay(cap, fields=fields)
+    model = O.RingModel(cap)
+    store = np.zeros((cap, 64), np.uint8)
+    for step in range(9):      # wraps the ring once
+        x = torch.from_numpy(rng.integers(0, 256, size=(n, 64), dtype=np.uint8)).pin_memory()
+        a = torch.from_numpy(rng.integers(0, 6, size=n).astype(np.int32)).pin_memory()
+        p = _rand_prios(rng, n)
+        rep.push_begin([x, a], n)
+        slots = (model.head + np.arange(n)) % cap
+        reserved = rep.priorities().cpu().numpy()
+        assert (reserved[slots] == 0).all()                      # retired before the copy may land
+        if model.size:
+            idx, _, _ = rep.sample(256)
+            assert not np.isin(idx.cpu().numpy(), slots).any()   # never sampled while being overwritten
+        rep.push_commit(torch.from_numpy(p))
+        model.push(p); store[slots] = x.numpy()
+        assert len(rep) == model.size and rep.head == model.head
+        np.testing.assert_array_equal(rep.priorities().cpu().numpy(), model.prios)
+        idx, _, _ = rep.sample(128)
+        np.testing.assert_array_equal(rep.gather(idx)["x"].cpu().numpy(), store[idx.cpu().numpy()])
+    rep.close()
+
+
 def test_empty_replay_sampling_is_an_error(R):
     from distributed_rl_b200._lib import B2RLError
     rep = R.DeviceReplay(16, fields=())
