@@ -43,7 +43,8 @@ constexpr int TILE_M = 128;
 constexpr int TILES = (POS + TILE_M - 1) / TILE_M; // 4 (the last one has 16 valid rows)
 constexpr int NSPLIT = 4;
 constexpr int N_PER_NET = NSPLIT * C_OUT;          // 128 MMA columns per network
-constexpr int A_STAGES = 3;
+constexpr int A_STAGES = 2;
+constexpr int STAGE_OUT_BYTES = 4 * 32 * 128;      // epilogue staging: 4 warps x 32 rows x 128 B
 constexpr int A_TILE_BYTES = TILE_M * K_TOTAL;     // 32 768: 2 K-chunks x 128 rows x 128 B
 constexpr int A_CHUNK_BYTES = TILE_M * 128;        // 16 384
 constexpr int RAW_STRIDE = 28288;                  // FRAME_BYTES rounded up to 128
@@ -168,6 +169,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
   uint8_t* sB = smem;
   uint8_t* sA = smem + B_BYTES;
   uint8_t* sRaw = sA + A_STAGES * A_TILE_BYTES;
+  uint8_t* sOut = sRaw + 2 * RAW_STRIDE;       // per-epilogue-warp 4 KiB transpose buffers
   __shared__ __align__(8) uint64_t b_full, raw_full[2], raw_empty[2], a_full[A_STAGES], a_empty[A_STAGES],
       t_full[2], t_empty[2];
   __shared__ uint32_t s_tmem;
@@ -308,38 +310,56 @@ k_conv1_fused(const __grid_constant__ Params P) {
         tc_fence_after();
         const int p = t * TILE_M + r_local;
         const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N_TOTAL);
+        uint8_t* stg = sOut + wq * 4096;            // this warp's 32 rows x 128 B, 16-byte units XOR-swizzled
+        const int rows_valid = POS - (t * TILE_M + wq * 32);   // rows of this warp's block that exist (<= 0: none)
 #pragma unroll
         for (int net = 0; net < N_NETS; ++net) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             int32_t q0[16], q1[16], q2[16], q3[16];
             const uint32_t col = tbase + net * N_PER_NET + h * 16;
+            const long long e0 = clock64();
             tc_ld16(col + 0 * C_OUT, q0);
             tc_ld16(col + 1 * C_OUT, q1);
             tc_ld16(col + 2 * C_OUT, q2);
             tc_ld16(col + 3 * C_OUT, q3);
             tc_wait_ld();
-            if (p < POS) {
-              float* o = P.out + (((int64_t)net * P.n + k) * POS + p) * C_OUT + h * 16;
-              const float* sc = s_scale + net * C_OUT + h * 16;
+            if (P.dbg && r_local == 0) P.dbg[blockIdx.x * 16 + 11] += clock64() - e0;
+            const float* sc = s_scale + net * C_OUT + h * 16;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float y[4];
+            for (int g = 0; g < 4; ++g) {
+              float y[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int i = g * 4 + e;
-                  // exact integers (< 2^24) recombined smallest digit first
-                  // (the power-of-two products are exact, so each fused step rounds once like mul+add)
-                  float v = __fmaf_rn((float)q2[i], 1.0f / 16384.0f, (float)q3[i] * (1.0f / 2097152.0f));
-                  v = __fmaf_rn((float)q1[i], 1.0f / 128.0f, v);
-                  v = v + (float)q0[i];
-                  v = v * sc[i];
-                  y[e] = (P.relu && v < 0.0f) ? 0.0f : v;
-                }
-                *reinterpret_cast<float4*>(o + g * 4) = make_float4(y[0], y[1], y[2], y[3]);
+              for (int e = 0; e < 4; ++e) {
+                const int i = g * 4 + e;
+                // exact integers (< 2^24) recombined smallest digit first
+                // (the power-of-two products are exact, so each fused step rounds once like mul+add)
+                float v = __fmaf_rn((float)q2[i], 1.0f / 16384.0f, (float)q3[i] * (1.0f / 2097152.0f));
+                v = __fmaf_rn((float)q1[i], 1.0f / 128.0f, v);
+                v = v + (float)q0[i];
+                v = v * sc[i];
+                y[e] = (P.relu && v < 0.0f) ? 0.0f : v;
+              }
+              const int unit = h * 4 + g;            // 16-byte unit of this row's 128 B
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
+                  make_float4(y[0], y[1], y[2], y[3]);
+            }
+          }
+          __syncwarp();
+          // the warp's 32 rows are 4 KiB contiguous in the NHWC output: 8 fully coalesced 512-byte stores
+          if (rows_valid > 0) {
+            float* obase = P.out + (((int64_t)net * P.n + k) * POS + (t * TILE_M + wq * 32)) * C_OUT;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int off = (i * 32 + lane) * 16;          // byte offset inside the 4 KiB block
+              const int row = off >> 7, unit = (off >> 4) & 7;
+              if (row < rows_valid) {
+                const float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+                *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(obase) + off) = v;
               }
             }
           }
+          __syncwarp();
         }
         tc_fence_before();
         mbar_arrive(&t_empty[acc]);
@@ -359,7 +379,8 @@ k_conv1_fused(const __grid_constant__ Params P) {
 
 template <int N_NETS>
 constexpr size_t smem_bytes() {
-  return (size_t)N_NETS * N_PER_NET * K_TOTAL + (size_t)A_STAGES * A_TILE_BYTES + 2 * (size_t)RAW_STRIDE + 1024;
+  return (size_t)N_NETS * N_PER_NET * K_TOTAL + (size_t)A_STAGES * A_TILE_BYTES + 2 * (size_t)RAW_STRIDE +
+         (size_t)STAGE_OUT_BYTES + 1024;
 }
 
 }  // namespace conv1
@@ -414,10 +435,10 @@ extern "C" int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, con
   if (dbg_buf) {   // profiling aid: per-role cycle counters of CTA 0 (synchronous; never set in production)
     long long h[16];
     B2RL_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-    static const char* names[10] = {"loader:wait raw_empty", "mma:wait t_empty", "mma:wait a_full", "mma:issue+commit",
+    static const char* names[12] = {"loader:wait raw_empty", "mma:wait t_empty", "mma:wait a_full", "mma:issue+commit",
                                     "prod:wait raw_full", "prod:wait a_empty", "prod:build", "prod:fence+arrive",
-                                    "epi:wait t_full", "epi:work"};
-    for (int i = 0; i < 10; ++i)
+                                    "epi:wait t_full", "epi:work", "(unused)", "epi:tcgen05.ld+wait"};
+    for (int i = 0; i < 12; ++i)
       fprintf(stderr, "[conv1 dbg] n_nets %d n %lld %-24s %lld\n", n_nets, (long long)n, names[i], h[i]);
   }
   return B2RL_OK;
