@@ -174,7 +174,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
       t_full[2], t_empty[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_scale[2 * C_OUT];
-  if (threadIdx.x < N_NETS * C_OUT) s_scale[threadIdx.x] = P.scale[threadIdx.x];
+  if (threadIdx.x < N_NETS * C_OUT) s_scale[threadIdx.x] = P.scale[threadIdx.x] * (1.0f / 128.0f);   // exact
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -311,6 +311,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
         const int p = t * TILE_M + r_local;
         const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N_TOTAL);
         uint8_t* stg = sOut + wq * 4096;            // this warp's 32 rows x 128 B, 16-byte units XOR-swizzled
+        const float relu_floor = P.relu ? 0.0f : -INFINITY;
         const int rows_valid = POS - (t * TILE_M + wq * 32);   // rows of this warp's block that exist (<= 0: none)
 #pragma unroll
         for (int net = 0; net < N_NETS; ++net) {
@@ -332,13 +333,13 @@ k_conv1_fused(const __grid_constant__ Params P) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int i = g * 4 + e;
-                // exact integers (< 2^24) recombined smallest digit first
-                // (the power-of-two products are exact, so each fused step rounds once like mul+add)
-                float v = __fmaf_rn((float)q2[i], 1.0f / 16384.0f, (float)q3[i] * (1.0f / 2097152.0f));
-                v = __fmaf_rn((float)q1[i], 1.0f / 128.0f, v);
-                v = v + (float)q0[i];
-                v = v * sc[i];
-                y[e] = (P.relu && v < 0.0f) ? 0.0f : v;
+                // digits are recombined pairwise in exact integer arithmetic (|u| < 2^31):
+                //   u = q0*2^7 + q1,  t = q2*2^7 + q3,   sum = (u + t*2^-14) * 2^-7
+                // one fp32 rounding per conversion (2^-24 relative), then one FMA and the scale.
+                const float fu = (float)(q0[i] * 128 + q1[i]);
+                const float ft = (float)(q2[i] * 128 + q3[i]);
+                const float v = __fmaf_rn(ft, 1.0f / 16384.0f, fu) * sc[i];   // sc already holds s_c / (255 * 2^7)
+                y[e] = fmaxf(v, relu_floor);
               }
               const int unit = h * 4 + g;            // 16-byte unit of this row's 128 B
               *reinterpret_cast<float4*>(stg + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
