@@ -27,7 +27,9 @@
 //   warp 2       TMEM allocator
 //   warps 4-11   im2col producers: SMEM frame -> 128B-swizzled K-major A tile (uint8);
 //                thread = (tile row, channel pair)
-//   warps 12-15  epilogue: tcgen05.ld -> recombine digits -> scale -> ReLU -> global
+//   warps 12-19  epilogue, two groups of 4 (one per TMEM lane quarter): group g takes network g
+//                (two nets) or channel half g (one net): tcgen05.ld -> recombine digits -> scale ->
+//                ReLU -> swizzled SMEM block -> coalesced 512-byte global stores
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -44,11 +46,11 @@ constexpr int TILES = (POS + TILE_M - 1) / TILE_M; // 4 (the last one has 16 val
 constexpr int NSPLIT = 4;
 constexpr int N_PER_NET = NSPLIT * C_OUT;          // 128 MMA columns per network
 constexpr int A_STAGES = 2;
-constexpr int STAGE_OUT_BYTES = 4 * 32 * 128;      // epilogue staging: 4 warps x 32 rows x 128 B
+constexpr int STAGE_OUT_BYTES = 8 * 32 * 128;      // epilogue staging: 8 warps x 32 rows x 128 B
 constexpr int A_TILE_BYTES = TILE_M * K_TOTAL;     // 32 768: 2 K-chunks x 128 rows x 128 B
 constexpr int A_CHUNK_BYTES = TILE_M * 128;        // 16 384
 constexpr int RAW_STRIDE = 28288;                  // FRAME_BYTES rounded up to 128
-constexpr int THREADS = 512;
+constexpr int THREADS = 640;                       // 20 warps: 3 role warps, 1 spare, 8 producers, 8 epilogue
 constexpr int PRODUCERS = 256;
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -181,7 +183,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
     mbar_init(&b_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], PRODUCERS); }
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], PRODUCERS); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -299,7 +301,9 @@ k_conv1_fused(const __grid_constant__ Params P) {
   } else if (warp >= 12) {
     // ------------------------------- epilogue -------------------------------
     const int wq = warp & 3;                     // TMEM lane quarter this warp may access
+    const int eg = (warp - 12) >> 2;             // epilogue group 0 / 1
     const int r_local = wq * 32 + lane;
+    const bool probe_e = P.dbg && r_local == 0 && eg == 0;
     int at = 0;
     for (int64_t k = first; k < P.n; k += stride) {
       for (int t = 0; t < TILES; ++t, ++at) {
@@ -310,13 +314,16 @@ k_conv1_fused(const __grid_constant__ Params P) {
         tc_fence_after();
         const int p = t * TILE_M + r_local;
         const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N_TOTAL);
-        uint8_t* stg = sOut + wq * 4096;            // this warp's 32 rows x 128 B, 16-byte units XOR-swizzled
+        uint8_t* stg = sOut + (eg * 4 + wq) * 4096; // this warp's 32 rows x 128 B, 16-byte units XOR-swizzled
         const float relu_floor = P.relu ? 0.0f : -INFINITY;
         const int rows_valid = POS - (t * TILE_M + wq * 32);   // rows of this warp's block that exist (<= 0: none)
+        {
+          const int net = (N_NETS == 2) ? eg : 0;
+          const int h_lo = (N_NETS == 2) ? 0 : eg, h_hi = (N_NETS == 2) ? 2 : eg + 1;
 #pragma unroll
-        for (int net = 0; net < N_NETS; ++net) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int hh = 0; hh < 2; ++hh) {
+            const int h = (N_NETS == 2) ? hh : eg;
+            if (hh >= h_hi - h_lo) break;
             int32_t q0[16], q1[16], q2[16], q3[16];
             const uint32_t col = tbase + net * N_PER_NET + h * 16;
             const long long e0 = clock64();
@@ -325,7 +332,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
             tc_ld16(col + 2 * C_OUT, q2);
             tc_ld16(col + 3 * C_OUT, q3);
             tc_wait_ld();
-            if (P.dbg && r_local == 0) P.dbg[blockIdx.x * 16 + 11] += clock64() - e0;
+            if (probe_e) P.dbg[blockIdx.x * 16 + 11] += clock64() - e0;
             const float* sc = s_scale + net * C_OUT + h * 16;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -354,7 +361,8 @@ k_conv1_fused(const __grid_constant__ Params P) {
             for (int i = 0; i < 8; ++i) {
               const int off = (i * 32 + lane) * 16;          // byte offset inside the 4 KiB block
               const int row = off >> 7, unit = (off >> 4) & 7;
-              if (row < rows_valid) {
+              const bool mine = (N_NETS == 2) || ((unit >> 2) == eg);   // one net: this group owns one channel half
+              if (row < rows_valid && mine) {
                 const float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
                 *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(obase) + off) = v;
               }
@@ -364,7 +372,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
         }
         tc_fence_before();
         mbar_arrive(&t_empty[acc]);
-        if (P.dbg && r_local == 0) {
+        if (probe_e) {
           P.dbg[blockIdx.x * 16 + 8] += c1 - c0;
           P.dbg[blockIdx.x * 16 + 9] += clock64() - c1;
         }
