@@ -28,7 +28,7 @@
 //   warps 4-11   im2col producers: SMEM frame -> 128B-swizzled K-major A tile (uint8);
 //                thread = (tile row, channel pair)
 //   warps 12-19  epilogue, two groups of 4 (one per TMEM lane quarter): group g takes network g
-//                (two nets) or channel half g (one net): tcgen05.ld -> recombine digits -> scale ->
+//                (with one network group 1 idles): tcgen05.ld -> recombine digits -> scale ->
 //                ReLU -> swizzled SMEM block -> coalesced 512-byte global stores
 #include "common.cuh"
 
@@ -319,11 +319,10 @@ k_conv1_fused(const __grid_constant__ Params P) {
         const int rows_valid = POS - (t * TILE_M + wq * 32);   // rows of this warp's block that exist (<= 0: none)
         {
           const int net = (N_NETS == 2) ? eg : 0;
-          const int h_lo = (N_NETS == 2) ? 0 : eg, h_hi = (N_NETS == 2) ? 2 : eg + 1;
+          const bool active = (N_NETS == 2) || eg == 0;   // one network: group 0 does it all (full-line stores)
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int h = (N_NETS == 2) ? hh : eg;
-            if (hh >= h_hi - h_lo) break;
+          for (int h = 0; h < 2; ++h) {
+            if (!active) break;
             int32_t q0[16], q1[16], q2[16], q3[16];
             const uint32_t col = tbase + net * N_PER_NET + h * 16;
             const long long e0 = clock64();
@@ -361,8 +360,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
             for (int i = 0; i < 8; ++i) {
               const int off = (i * 32 + lane) * 16;          // byte offset inside the 4 KiB block
               const int row = off >> 7, unit = (off >> 4) & 7;
-              const bool mine = (N_NETS == 2) || ((unit >> 2) == eg);   // one net: this group owns one channel half
-              if (row < rows_valid && mine) {
+              if (row < rows_valid && active) {
                 const float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
                 *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(obase) + off) = v;
               }
