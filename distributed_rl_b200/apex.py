@@ -51,6 +51,7 @@ class ApexConfig:
     MODEL: dict = field(default_factory=lambda: default_apex_model())
     CHANNELS_LAST: bool = True      # NHWC activations/weights: cuDNN's TF32 kernels skip their layout transposes
     FUSED_CONV1: bool = True        # gather + conv_1 on the tcgen05 tensor cores (csrc/conv1.cu) in fused_step
+    FUSED_OPTIM: bool = True        # RMSprop + zero_grad + grad-norm in one launch (csrc/optim.cu)
 
     @staticmethod
     def from_configuration():
@@ -270,7 +271,16 @@ class Learner:
             self.target_model.to(memory_format=torch.channels_last)
 
     def build_optim(self):
-        self.optim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
+        info = self.cfg.OPTIM_INFO
+        fusable = (self.cfg.FUSED_OPTIM and info["name"] == "rmsprop" and not info.get("momentum", 0)
+                   and not info.get("decay", 0) and self.device.type == "cuda")
+        if fusable:
+            from .optim import FusedRMSprop
+            self.optim = FusedRMSprop(self.model.getParameters(), lr=info["lr"], alpha=info.get("alpha", 0.99),
+                                      eps=info.get("eps", 1e-5), centered=info.get("centered", False))
+        else:
+            self.optim = make_optimizer(info, self.model.getParameters())
+        self._fused_optim = fusable
 
     # -- one training step on an explicit minibatch (reference signature) -----------
     def _to_dev(self, x, dtype):
@@ -312,6 +322,8 @@ class Learner:
 
     def step(self):
         """Learner.step (:123-138): 'norm' = sqrt(sum_i ||g_i||_2) (sic), RMSprop, zero_grad."""
+        if self._fused_optim:
+            return {"p_norm": self.optim.step(want_norm=True)[0]}    # update + zero_grad + norm: one launch
         grads = [p.grad for p in self.model.parameters() if p.grad is not None]
         p_norm = torch.stack(torch._foreach_norm(grads, 2)).sum().sqrt()
         self.optim.step()

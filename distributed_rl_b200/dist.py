@@ -26,7 +26,9 @@ class FlatGradBucket:
         self.flat = torch.zeros(sum(p.numel() for p in self.params), device=device, dtype=self.params[0].dtype)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # same element order as the parameter (channels_last conv weights keep their strides), so that
+            # elementwise fused optimizers can walk param and grad storage together
+            p.grad = self.flat[off:off + p.numel()].as_strided(p.shape, p.stride())
             off += p.numel()
 
     def all_reduce_mean(self) -> None:

@@ -217,6 +217,18 @@ int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t*
                      const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, float* out_dev,
                      int32_t relu, void* stream);
 
+/* Learner.step (APE_X/Learner.py:123-138; IMPALA/Learner.py:258-266 without the clipping) with
+ * torch.optim.RMSprop's update (baseline/utils.py getOptim :124-130; centered for Ape-X,
+ * cfg/ape_x.json:27-35) in ONE pass: square_avg / grad_avg / param update, gradient zeroed, and
+ * the reference's diagnostic "norm" sqrt(sum_i ||g_i||_2) written to grad_norm_out_dev (may be
+ * NULL).  The four pointer arrays and numel are HOST arrays of n_tensors (<= 24) entries holding
+ * device pointers of dense tensors with identical element order; sumsq_scratch_dev: n_tensors
+ * doubles, zeroed once by the caller (the kernel re-zeroes them). */
+int b2rl_rmsprop_step(float* const* params, float* const* grads, float* const* square_avg,
+                      float* const* grad_avg, const int64_t* numel, int32_t n_tensors, float lr, float alpha,
+                      float eps, int32_t centered, double* sumsq_scratch_dev, float* grad_norm_out_dev,
+                      void* stream);
+
 /* Number of kernels this library has launched in this process (bench.py's
  * `gpu_launches`). */
 int64_t b2rl_launch_count(void);

@@ -236,3 +236,32 @@ def test_fused_conv1_step_equals_staged_step(apex):
     np.testing.assert_allclose(t0.cpu().numpy(), t1.cpu().numpy(), rtol=1e-3, atol=1e-5)
     for a, b in zip(p0, p1):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("centered,eps,alpha", [(True, 1.5e-7, 0.95), (False, 1e-5, 0.99)])
+def test_fused_rmsprop_matches_torch_optim(centered, eps, alpha):
+    """csrc/optim.cu == torch.optim.RMSprop (the optimiser getOptim builds, baseline/utils.py:124-130)
+    over 4 steps, including a channels_last conv weight; plus zero_grad and the reference's 'norm'."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributed_rl_b200.optim import FusedRMSprop
+    torch.manual_seed(0)
+    shapes = [(32, 4, 8, 8), (64, 32, 4, 4), (512, 3136), (6, 512), (1, 7)]
+    mine = [torch.randn(s, device="cuda") * 0.1 for s in shapes]
+    mine[1] = mine[1].contiguous(memory_format=torch.channels_last)
+    ref = [p.detach().clone(memory_format=torch.preserve_format).requires_grad_(True) for p in mine]
+    mine = [p.requires_grad_(True) for p in mine]
+    opt_ref = torch.optim.RMSprop(ref, lr=6.25e-5, alpha=alpha, eps=eps, centered=centered)
+    opt = FusedRMSprop(mine, lr=6.25e-5, alpha=alpha, eps=eps, centered=centered)
+    for step in range(4):
+        gs = [torch.randn_like(p) * (0.5 + step) for p in ref]
+        for p, q, g in zip(ref, mine, gs):
+            p.grad = g.clone(memory_format=torch.preserve_format)
+            q.grad.copy_(g)
+        want_norm = sum(g.norm(2) for g in gs) ** 0.5
+        norm = opt.step()
+        opt_ref.step()
+        np.testing.assert_allclose(float(norm), float(want_norm), rtol=1e-6)
+        for p, q in zip(ref, mine):
+            np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-6, atol=1e-9)
+            assert float(q.grad.abs().max()) == 0.0            # zero_grad fused
