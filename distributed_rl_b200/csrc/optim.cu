@@ -25,7 +25,7 @@ struct OptTable {
 };
 
 __global__ void __launch_bounds__(OPT_THREADS)
-k_rmsprop(const __grid_constant__ OptTable T, float lr, float alpha, float eps, int centered,
+k_rmsprop(const __grid_constant__ OptTable T, float lr, float alpha, float one_m_alpha, float eps, int centered,
           double* __restrict__ sumsq /*[n_tensors] or nullptr*/) {
   __shared__ double s_part[OPT_THREADS / 32];
   int t = 0;
@@ -36,7 +36,6 @@ k_rmsprop(const __grid_constant__ OptTable T, float lr, float alpha, float eps, 
   float* __restrict__ G = T.g[t];
   float* __restrict__ SQ = T.sq[t];
   float* __restrict__ GA = T.ga[t];
-  const float one_m_alpha = 1.0f - alpha;
   double acc = 0.0;
 #pragma unroll
   for (int u = 0; u < OPT_PER_THREAD; ++u) {
@@ -84,8 +83,8 @@ __global__ void k_grad_norm_finish(double* __restrict__ sumsq, int n, float* __r
 using namespace b2rl;
 
 extern "C" int b2rl_rmsprop_step(float* const* params, float* const* grads, float* const* square_avg,
-                                 float* const* grad_avg, const int64_t* numel, int32_t n_tensors, float lr,
-                                 float alpha, float eps, int32_t centered, double* sumsq_scratch_dev,
+                                 float* const* grad_avg, const int64_t* numel, int32_t n_tensors, double lr,
+                                 double alpha, double eps, int32_t centered, double* sumsq_scratch_dev,
                                  float* grad_norm_out_dev, void* stream) {
   B2RL_REQUIRE(n_tensors >= 1 && n_tensors <= OPT_MAX_TENSORS, "1..24 tensors");
   B2RL_REQUIRE(params && grads && square_avg && numel, "null argument");
@@ -106,7 +105,9 @@ extern "C" int b2rl_rmsprop_step(float* const* params, float* const* grads, floa
   T.block_start[n_tensors] = (int32_t)blocks;
   B2RL_REQUIRE(blocks < (1LL << 31), "too many elements");
   cudaStream_t st = (cudaStream_t)stream;
-  k_rmsprop<<<(unsigned)blocks, OPT_THREADS, 0, st>>>(T, lr, alpha, eps, centered, sumsq_scratch_dev);
+  // python-double hyper-parameters, cast once like torch's foreach kernels do (1 - alpha formed in double)
+  k_rmsprop<<<(unsigned)blocks, OPT_THREADS, 0, st>>>(T, (float)lr, (float)alpha, (float)(1.0 - alpha), (float)eps,
+                                                      centered, sumsq_scratch_dev);
   count_launch();
   if (grad_norm_out_dev) {
     k_grad_norm_finish<<<1, 32, 0, st>>>(sumsq_scratch_dev, n_tensors, grad_norm_out_dev);

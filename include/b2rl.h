@@ -225,8 +225,8 @@ int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t*
  * device pointers of dense tensors with identical element order; sumsq_scratch_dev: n_tensors
  * doubles, zeroed once by the caller (the kernel re-zeroes them). */
 int b2rl_rmsprop_step(float* const* params, float* const* grads, float* const* square_avg,
-                      float* const* grad_avg, const int64_t* numel, int32_t n_tensors, float lr, float alpha,
-                      float eps, int32_t centered, double* sumsq_scratch_dev, float* grad_norm_out_dev,
+                      float* const* grad_avg, const int64_t* numel, int32_t n_tensors, double lr, double alpha,
+                      double eps, int32_t centered, double* sumsq_scratch_dev, float* grad_norm_out_dev,
                       void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py's
