@@ -39,7 +39,7 @@ def test_apex_2pow20_slots_full_payload(R):
         idx, prob, w = rep.sample(n)
         i = idx.cpu().numpy()
         assert i.min() >= 0 and i.max() < N
-        np.testing.assert_array_equal(prob.cpu().numpy(), (p[idx] / np.float32(st[0])).cpu().numpy())
+        np.testing.assert_array_equal(prob.cpu().numpy(), p[idx].cpu().numpy() / np.float32(st[0]))   # IEEE fp32 division
         assert float(w.max()) <= 1.0 + 1e-6 and float(w.min()) > 0
         out = rep.gather(idx)
         sub = np.random.default_rng(n).choice(n, size=64, replace=False)       # hash 64 rows on the host
