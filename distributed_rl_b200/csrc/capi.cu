@@ -27,8 +27,7 @@ extern "C" int64_t b2rl_launch_count(void) { return g_launches.load(std::memory_
 static void free_all(b2rl_replay* h) {
   for (int f = 0; f < B2RL_MAX_FIELDS; ++f)
     if (h->field[f]) cudaFree(h->field[f]);
-  if (h->sum) cudaFree(h->sum);
-  if (h->minv) cudaFree(h->minv);
+  if (h->node) cudaFree(h->node);
   if (h->tag) cudaFree(h->tag);
   if (h->mark) cudaFree(h->mark);
   if (h->scratch_val) cudaFree(h->scratch_val);
@@ -61,12 +60,11 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
     // +16 B so a 16-byte bulk/vector access on the last row never leaves the allocation
     alloc((void**)&h->field[f], (size_t)d->capacity * (size_t)d->field_bytes[f] + 16);
   }
-  alloc((void**)&h->sum, sizeof(double) * 2 * (size_t)h->cap2);
-  alloc((void**)&h->minv, sizeof(float) * 2 * (size_t)h->cap2);
+  alloc((void**)&h->node, sizeof(TreeNode) * 2 * (size_t)h->cap2);
   alloc((void**)&h->tag, sizeof(uint32_t) * (size_t)h->cap2);
   alloc((void**)&h->mark, sizeof(int32_t) * (size_t)h->cap2);
   alloc((void**)&h->scratch_val, sizeof(float) * (size_t)h->capacity);
-  alloc((void**)&h->rng_dev, sizeof(uint64_t) * 2);
+  alloc((void**)&h->rng_dev, sizeof(uint64_t) * 3);   // {seed, counter, last-block ticket}
   if (e != cudaSuccess) {
     set_error("cudaMalloc failed while creating a %lld-slot replay: %s", (long long)d->capacity,
               cudaGetErrorString(e));
@@ -76,12 +74,14 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
     return B2RL_ERR_NOMEM;
   }
   // empty tree: sums 0, mins +inf, tags/marks 0
-  B2RL_CUDA(cudaMemset(h->sum, 0, sizeof(double) * 2 * (size_t)h->cap2));
-  B2RL_CUDA(cudaMemset(h->minv, 0x7f, sizeof(float) * 2 * (size_t)h->cap2));  // 0x7f7f7f7f ~ 3.4e38
+  {
+    int rc = b2rl_tree_build(h, nullptr, 0, nullptr);   // empty tree: sums 0, mins +inf
+    if (rc != B2RL_OK) { free_all(h); delete h; return rc; }
+  }
   B2RL_CUDA(cudaMemset(h->tag, 0, sizeof(uint32_t) * (size_t)h->cap2));
   B2RL_CUDA(cudaMemset(h->mark, 0, sizeof(int32_t) * (size_t)h->cap2));
   {
-    const uint64_t init[2] = {1234ULL, 0ULL};
+    const uint64_t init[3] = {1234ULL, 0ULL, 0ULL};
     B2RL_CUDA(cudaMemcpy(h->rng_dev, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   B2RL_CUDA(cudaDeviceSynchronize());

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
 
 #include "../../include/b2rl.h"
@@ -96,6 +97,32 @@ __host__ __device__ __forceinline__ double philox_u01(uint64_t seed, uint64_t ct
 
 }  // namespace b2rl
 
+// One sum-tree node: subtree sum (fp64) and subtree min over valid (p > 0) leaves (fp32) in ONE
+// 16-byte record, so a path update or a descent touches one sector per node instead of two.
+struct __align__(16) TreeNode {
+  double s;
+  float m;
+  float pad;
+};
+__device__ __forceinline__ TreeNode ld_node(const TreeNode* p) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  TreeNode n;
+  memcpy(&n, &v, sizeof(n));
+  return n;
+}
+__device__ __forceinline__ TreeNode ld_node_cg(const TreeNode* p) {   // L2 only: node may be written by another SM
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  TreeNode n;
+  memcpy(&n, &v, sizeof(n));
+  return n;
+}
+__device__ __forceinline__ void st_node(TreeNode* p, double s, float m) {
+  TreeNode n{s, m, 0.0f};
+  float4 v;
+  memcpy(&v, &n, sizeof(n));
+  *reinterpret_cast<float4*>(p) = v;
+}
+
 // The opaque handle.
 struct b2rl_replay {
   int device = 0;
@@ -105,13 +132,12 @@ struct b2rl_replay {
   int n_fields = 0;
   int64_t field_bytes[B2RL_MAX_FIELDS] = {0};
   uint8_t* field[B2RL_MAX_FIELDS] = {nullptr};
-  double* sum = nullptr;      // [2*cap2] implicit heap, node 1 = root, leaf j = cap2 + j
-  float* minv = nullptr;      // [2*cap2] min over valid (p > 0) leaves, +inf otherwise
+  TreeNode* node = nullptr;   // [2*cap2] implicit heap, node 1 = root, leaf j = cap2 + j
   uint32_t* tag = nullptr;    // [cap2]   last-writer tags, self-cleaning
   int32_t* mark = nullptr;    // [cap2]   per-internal-node side bits + arrival count, self-cleaning
   int64_t* scratch_idx = nullptr;  // [capacity] ring indices for push/evict
   float* scratch_val = nullptr;    // [capacity]
-  uint64_t* rng_dev = nullptr;     // [2] device-resident Philox stream {seed, counter}
+  uint64_t* rng_dev = nullptr;     // [3] device-resident Philox stream {seed, counter, ticket}
   int64_t size = 0;       // valid slots
   int64_t head = 0;       // next slot to write
   int64_t reserved = 0;   // slots zeroed by b2rl_replay_reserve and not yet committed

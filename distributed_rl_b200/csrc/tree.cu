@@ -30,8 +30,7 @@ constexpr int BUILD_PER_THREAD = BUILD_CHUNK / 2 / BUILD_THREADS;  // 4
 // fp64 leaves, reduces the bottom levels of its subtree in shared memory and
 // writes every node out; its subtree root lands at heap index cap2/2048 + c.
 __global__ void __launch_bounds__(BUILD_THREADS)
-k_build_bottom(const float* __restrict__ prios, int64_t n_valid, double* __restrict__ sum,
-               float* __restrict__ minv, int64_t cap2) {
+k_build_bottom(const float* __restrict__ prios, int64_t n_valid, TreeNode* __restrict__ node, int64_t cap2) {
   __shared__ double s_sum[BUILD_CHUNK];
   __shared__ float s_min[BUILD_CHUNK];
   const int64_t leaf0 = (int64_t)blockIdx.x * BUILD_CHUNK;
@@ -42,8 +41,7 @@ k_build_bottom(const float* __restrict__ prios, int64_t n_valid, double* __restr
     const float m = (p > 0.0f) ? p : INFINITY;
     s_sum[i] = (double)p;
     s_min[i] = m;
-    sum[cap2 + j] = (double)p;
-    minv[cap2 + j] = m;
+    st_node(node + cap2 + j, (double)p, m);
   }
   __syncthreads();
   int per = 2;  // leaves per node of the level being produced
@@ -61,8 +59,7 @@ k_build_bottom(const float* __restrict__ prios, int64_t n_valid, double* __restr
     for (int i = threadIdx.x; i < w; i += BUILD_THREADS, ++c) {
       s_sum[i] = ts[c];
       s_min[i] = tm[c];
-      sum[base + i] = ts[c];
-      minv[base + i] = tm[c];
+      st_node(node + base + i, ts[c], tm[c]);
     }
     __syncthreads();
   }
@@ -71,18 +68,16 @@ k_build_bottom(const float* __restrict__ prios, int64_t n_valid, double* __restr
 // Levels above the 2048-leaf subtrees: `m` = cap2/2048 nodes on the deepest of
 // them.  One CTA, level-synchronous (at most 12 levels for cap2 = 2^23).
 __global__ void __launch_bounds__(1024)
-k_build_top(double* __restrict__ sum, float* __restrict__ minv, int64_t m) {
+k_build_top(TreeNode* __restrict__ node, int64_t m) {
   for (int64_t w = m / 2; w >= 1; w >>= 1) {
     for (int64_t i = threadIdx.x; i < w; i += blockDim.x) {
-      const int64_t node = w + i;
-      const double2 c = *reinterpret_cast<const double2*>(sum + 2 * node);
-      const float2 mm = *reinterpret_cast<const float2*>(minv + 2 * node);
-      sum[node] = c.x + c.y;
-      minv[node] = fminf(mm.x, mm.y);
+      const int64_t nd = w + i;
+      const TreeNode a = ld_node(node + 2 * nd), b = ld_node(node + 2 * nd + 1);
+      st_node(node + nd, a.s + b.s, fminf(a.m, b.m));
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { sum[0] = 0.0; minv[0] = INFINITY; }
+  if (threadIdx.x == 0) st_node(node, 0.0, INFINITY);
 }
 
 // ----------------------------------------------------------------------------
@@ -91,24 +86,39 @@ k_build_top(double* __restrict__ sum, float* __restrict__ minv, int64_t m) {
 constexpr int SAMPLE_THREADS = 128;
 
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-k_tree_sample(const double* __restrict__ sum, const float* __restrict__ minv, int64_t cap2,
+k_tree_sample(const TreeNode* __restrict__ node, int64_t cap2,
               int levels, const double* __restrict__ u01, uint64_t seed, uint64_t rng_offset,
               const uint64_t* __restrict__ rng_state, int64_t n, float n_valid, float beta,
               const float* __restrict__ max_w_ext, int64_t* __restrict__ idx_out,
               float* __restrict__ prob_out, float* __restrict__ w_out) {
   const int64_t k = (int64_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x;
+  if (rng_state) {
+    // device-resident Philox stream: every block reads {seed, counter}; the LAST block to have done
+    // so advances the counter by n (and re-arms the ticket), so no separate launch is needed.
+    seed = rng_state[0];
+    rng_offset = rng_state[1];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(const_cast<uint64_t*>(rng_state) + 2);
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        const_cast<uint64_t*>(rng_state)[1] = rng_offset + (uint64_t)n;
+        *ticket = 0u;
+      }
+    }
+  }
   if (k >= n) return;
-  const double root = sum[1];
-  if (rng_state) { seed = rng_state[0]; rng_offset = rng_state[1]; }
+  const TreeNode rootn = ld_node(node + 1);
+  const double root = rootn.s;
   const double u = u01 ? u01[k] : philox_u01(seed, rng_offset + (uint64_t)k);
   double pos = __dmul_rn(root, u);  // np.random.uniform(0, root) == root * random_sample()
   int64_t i = 1;
   for (int l = 0; l < levels; ++l) {
-    const double2 c = *reinterpret_cast<const double2*>(sum + 2 * i);
-    // Node._find: left iff pos < left.  The `c.y == 0` guard only matters when
+    const double cl = node[2 * i].s, cr = node[2 * i + 1].s;   // both children live in one 32-byte sector
+    // Node._find: left iff pos < left.  The `cr == 0` guard only matters when
     // pos rounds up to the subtree total (the reference dereferences None there).
-    const bool left = (pos < c.x) || (c.y == 0.0);
-    if (!left) pos = __dsub_rn(pos, c.x);
+    const bool left = (pos < cl) || (cr == 0.0);
+    if (!left) pos = __dsub_rn(pos, cl);
     i = 2 * i + (left ? 0 : 1);
   }
   const int64_t j = i - cap2;
@@ -116,7 +126,7 @@ k_tree_sample(const double* __restrict__ sum, const float* __restrict__ minv, in
   if (prob_out == nullptr && w_out == nullptr) return;
   // APE_X/ReplayMemory.py:65-67, baseline/PER.py:98,129-133 — fp32 op by op.
   const float s32 = (float)root;
-  const float p = (float)sum[i];
+  const float p = (float)node[i].s;
   const float prob = __fdiv_rn(p, s32);
   if (prob_out) prob_out[k] = prob;
   if (w_out) {
@@ -125,7 +135,7 @@ k_tree_sample(const double* __restrict__ sum, const float* __restrict__ minv, in
     if (max_w_ext) {
       max_w = *max_w_ext;
     } else {
-      const float min_prob = __fdiv_rn(minv[1], s32);
+      const float min_prob = __fdiv_rn(rootn.m, s32);
       max_w = powcr(__fmul_rn(n_valid, min_prob), -beta);
     }
     w_out[k] = __fdiv_rn(w_un, max_w);
@@ -134,7 +144,7 @@ k_tree_sample(const double* __restrict__ sum, const float* __restrict__ minv, in
 
 __global__ void k_rng_advance(uint64_t* __restrict__ rng_state, uint64_t n) { rng_state[1] += n; }
 __global__ void k_rng_seed(uint64_t* __restrict__ rng_state, uint64_t seed, uint64_t ctr) {
-  rng_state[0] = seed; rng_state[1] = ctr;
+  rng_state[0] = seed; rng_state[1] = ctr; rng_state[2] = 0;
 }
 
 __global__ void k_philox_uniforms(uint64_t seed, uint64_t off, int64_t n, double* __restrict__ out) {
@@ -142,21 +152,21 @@ __global__ void k_philox_uniforms(uint64_t seed, uint64_t off, int64_t n, double
   if (k < n) out[k] = philox_u01(seed, off + (uint64_t)k);
 }
 
-__global__ void k_tree_stats(const double* __restrict__ sum, const float* __restrict__ minv,
-                             float n_valid, float beta, double* __restrict__ out,
-                             float* __restrict__ max_w_out) {
-  const double root = sum[1];
+__global__ void k_tree_stats(const TreeNode* __restrict__ node, float n_valid, float beta,
+                             double* __restrict__ out, float* __restrict__ max_w_out) {
+  const TreeNode r = ld_node(node + 1);
+  const double root = r.s;
   const float s32 = (float)root;
-  const float mn = minv[1];
+  const float mn = r.m;
   const float mw = powcr(__fmul_rn(n_valid, __fdiv_rn(mn, s32)), -beta);
   if (out) { out[0] = root; out[1] = (double)mn; out[2] = (double)mw; }
   if (max_w_out) *max_w_out = mw;
 }
 
-__global__ void k_tree_leaves(const double* __restrict__ sum, int64_t cap2, int64_t start, int64_t n,
+__global__ void k_tree_leaves(const TreeNode* __restrict__ node, int64_t cap2, int64_t start, int64_t n,
                               float* __restrict__ out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) out[k] = (float)sum[cap2 + start + k];
+  if (k < n) out[k] = (float)node[cap2 + start + k].s;
 }
 
 // ----------------------------------------------------------------------------
@@ -193,7 +203,7 @@ k_update_tag(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capaci
 __global__ void __launch_bounds__(UPD_THREADS)
 k_update_write(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
                const float* __restrict__ vals, float const_val, int64_t n,
-               const uint32_t* __restrict__ tag, double* __restrict__ sum, float* __restrict__ minv,
+               const uint32_t* __restrict__ tag, TreeNode* __restrict__ tree,
                int32_t* __restrict__ mark, int64_t cap2, int levels) {
   const int64_t k = (int64_t)blockIdx.x * UPD_THREADS + threadIdx.x;
   if (k >= n) return;
@@ -202,8 +212,7 @@ k_update_write(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
   if (tag[j] != (uint32_t)(k + 1)) return;  // a later k wrote the same slot
   const float p = vals ? vals[k] : const_val;
   int64_t node = cap2 + j;
-  sum[node] = (double)p;
-  minv[node] = (p > 0.0f) ? p : INFINITY;
+  st_node(tree + node, (double)p, (p > 0.0f) ? p : INFINITY);
   for (int l = 0; l < levels; ++l) {
     const int bit = (node & 1) ? 2 : 1;
     node >>= 1;
@@ -214,7 +223,7 @@ k_update_write(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
 
 __global__ void __launch_bounds__(UPD_THREADS)
 k_update_climb(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity, int64_t n,
-               uint32_t* __restrict__ tag, double* __restrict__ sum, float* __restrict__ minv,
+               uint32_t* __restrict__ tag, TreeNode* __restrict__ tree,
                int32_t* __restrict__ mark, int64_t cap2, int levels) {
   const int64_t k = (int64_t)blockIdx.x * UPD_THREADS + threadIdx.x;
   if (k >= n) return;
@@ -229,10 +238,8 @@ k_update_climb(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
     const int old = atomicAdd(mark + node, 4);     // arrivals live above the two side bits
     if ((old >> 2) + 1 < __popc(old & 3)) return;  // the other touched child arrives later
     __threadfence();                               // acquire: see the other subtree's writes
-    const double2 c = __ldcg(reinterpret_cast<const double2*>(sum + 2 * node));
-    const float2 m = __ldcg(reinterpret_cast<const float2*>(minv + 2 * node));
-    sum[node] = c.x + c.y;
-    minv[node] = fminf(m.x, m.y);
+    const TreeNode a = ld_node_cg(tree + 2 * node), b = ld_node_cg(tree + 2 * node + 1);
+    st_node(tree + node, a.s + b.s, fminf(a.m, b.m));
     mark[node] = 0;                                // self-clean: nobody else visits this node now
   }
 }
@@ -255,8 +262,8 @@ constexpr int US_MAX_LEVELS = 24;
 
 __global__ void __launch_bounds__(US_THREADS, 1)
 k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
-                const float* __restrict__ vals, float const_val, int n, double* __restrict__ sum,
-                float* __restrict__ minv, int64_t cap2, int levels) {
+                const float* __restrict__ vals, float const_val, int n, TreeNode* __restrict__ tree,
+                int64_t cap2, int levels) {
   __shared__ uint64_t s_key[US_THREADS];
   __shared__ uint32_t s_leaf[US_THREADS];
   __shared__ float s_valf[US_THREADS];
@@ -306,8 +313,9 @@ k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t cap
   for (int l = 0; l < US_MAX_LEVELS; ++l) {
     if (valid && l < levels) {
       const int64_t node = ((cap2 + (int64_t)leaf) >> l) ^ 1;   // heap index of the sibling
-      pre_sum[l] = __ldcg(sum + node);
-      pre_min[l] = __ldcg(minv + node);
+      const TreeNode sib = ld_node_cg(tree + node);             // one 16-byte request per level
+      pre_sum[l] = sib.s;
+      pre_min[l] = sib.m;
     } else { pre_sum[l] = 0.0; pre_min[l] = INFINITY; }
   }
 
@@ -326,10 +334,7 @@ k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t cap
   const float vwin = valid ? s_valf[hi - 1] : 0.0f;          // last writer wins
   double cur_sum = (double)vwin;
   float cur_min = (vwin > 0.0f) ? vwin : INFINITY;
-  if (valid && t == lo) {
-    sum[cap2 + leaf] = cur_sum;
-    minv[cap2 + leaf] = cur_min;
-  }
+  if (valid && t == lo) st_node(tree + cap2 + leaf, cur_sum, cur_min);
 #pragma unroll
   for (int l = 0; l < US_MAX_LEVELS; ++l) {
     if (l >= levels) break;
@@ -353,9 +358,7 @@ k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t cap
     }
     __syncthreads();
     if (valid && t == lo) {
-      const int64_t parent = (cap2 + (int64_t)leaf) >> (l + 1);
-      sum[parent] = cur_sum;
-      minv[parent] = cur_min;
+      st_node(tree + ((cap2 + (int64_t)leaf) >> (l + 1)), cur_sum, cur_min);
     }
   }
 }
@@ -382,8 +385,8 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
       const int m = (int)((n - off < US_THREADS) ? (n - off) : US_THREADS);
       k_update_sorted<<<1, US_THREADS, 0, st>>>(idx_dev ? idx_dev + off : nullptr,
                                                 (ring_start + off) % h->capacity, h->capacity,
-                                                vals_dev ? vals_dev + off : nullptr, const_val, m, h->sum,
-                                                h->minv, h->cap2, h->levels);
+                                                vals_dev ? vals_dev + off : nullptr, const_val, m, h->node,
+                                                h->cap2, h->levels);
       count_launch();
     }
     B2RL_CHECK_LAUNCH();
@@ -392,9 +395,9 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
   const unsigned g = grid_for(n, UPD_THREADS);
   k_update_tag<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag);
   k_update_write<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, vals_dev, const_val, n,
-                                            h->tag, h->sum, h->minv, h->mark, h->cap2, h->levels);
-  k_update_climb<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag, h->sum,
-                                            h->minv, h->mark, h->cap2, h->levels);
+                                            h->tag, h->node, h->mark, h->cap2, h->levels);
+  k_update_climb<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag, h->node,
+                                            h->mark, h->cap2, h->levels);
   count_launch(3);
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
@@ -407,10 +410,10 @@ extern "C" int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t chunks = (h->cap2 + BUILD_CHUNK - 1) / BUILD_CHUNK;
-  k_build_bottom<<<(unsigned)chunks, BUILD_THREADS, 0, st>>>(prios_dev, n, h->sum, h->minv, h->cap2);
+  k_build_bottom<<<(unsigned)chunks, BUILD_THREADS, 0, st>>>(prios_dev, n, h->node, h->cap2);
   count_launch();
   if (h->cap2 > BUILD_CHUNK) {
-    k_build_top<<<1, 1024, 0, st>>>(h->sum, h->minv, h->cap2 / BUILD_CHUNK);
+    k_build_top<<<1, 1024, 0, st>>>(h->node, h->cap2 / BUILD_CHUNK);
     count_launch();
   }
   B2RL_CHECK_LAUNCH();
@@ -430,7 +433,7 @@ extern "C" int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t 
   if (n == 0) return B2RL_OK;
   DeviceGuard g(h->device);
   k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(
-      h->sum, h->minv, h->cap2, h->levels, u01_dev, seed, rng_offset, nullptr, n, (float)h->size, beta,
+      h->node, h->cap2, h->levels, u01_dev, seed, rng_offset, nullptr, n, (float)h->size, beta,
       max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
@@ -457,10 +460,9 @@ extern "C" int b2rl_tree_sample_stream(b2rl_replay* h, int64_t n, float beta, co
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, st>>>(
-      h->sum, h->minv, h->cap2, h->levels, nullptr, 0, 0, h->rng_dev, n, (float)h->size, beta,
+      h->node, h->cap2, h->levels, nullptr, 0, 0, h->rng_dev, n, (float)h->size, beta,
       max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
-  k_rng_advance<<<1, 1, 0, st>>>(h->rng_dev, (uint64_t)n);
-  count_launch(2);
+  count_launch();
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
 }
@@ -489,7 +491,7 @@ extern "C" int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev
                                void* stream) {
   B2RL_REQUIRE(h != nullptr && (stats_out_dev != nullptr || max_w_out_dev != nullptr), "null argument");
   DeviceGuard g(h->device);
-  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->sum, h->minv, (float)h->size, beta, stats_out_dev,
+  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->node, (float)h->size, beta, stats_out_dev,
                                                   max_w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
@@ -502,7 +504,7 @@ extern "C" int b2rl_tree_leaves(b2rl_replay* h, int64_t start, int64_t n, float*
   if (n == 0) return B2RL_OK;
   B2RL_REQUIRE(out_dev != nullptr, "null out");
   DeviceGuard g(h->device);
-  k_tree_leaves<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->sum, h->cap2, start, n, out_dev);
+  k_tree_leaves<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->node, h->cap2, start, n, out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;

@@ -110,7 +110,7 @@ def test_fused_graph_step_equals_eager_step(apex):
     for a, b in zip(pe, pg):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=5e-5)  # cuDNN picks algos per call
     assert (te != tg).float().mean() < 0.01       # same slots updated with (nearly) the same priorities
-    assert le == lg and le >= 5                   # sample + rng advance, gather, target, update
+    assert le == lg and le >= 4                   # sample, gather, target, update (+conv1/optimizer kernels)
 
 
 def test_r2d2_learner_train_matches_oracle_and_autograd():
