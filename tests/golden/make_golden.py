@@ -333,7 +333,57 @@ def gen_impala():
     print("impala.npz:", len(out), "arrays")
 
 
-GROUPS = {"tree": gen_tree, "apex": gen_apex, "r2d2": gen_r2d2, "impala": gen_impala}
+def seeded_weights(shapes, seed):
+    """Network weights that both the reference (here) and the GPU test can regenerate from a seed."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = []
+    for shp in shapes:
+        fan_in = int(np.prod(shp[1:]))
+        out.append((rng.uniform(-1, 1, size=shp) / np.sqrt(fan_in)).astype(np.float32))
+    return out
+
+
+def gen_apex_e2e():
+    """Whole reference Learner.train (CPU) — network forward x3, target, loss, backward, centered
+    RMSprop — on seeded weights and a seeded minibatch; records what train returns plus a slice of
+    every updated weight tensor.  The GPU test replays it through distributed_rl_b200.apex.Learner."""
+    import numpy as np
+    import torch
+    from oracle import ref_harness as H
+
+    H.enter_reference("ape_x.json")
+    import configuration as C  # type: ignore
+
+    B = 16
+    C.BATCHSIZE = B
+    l = H.bare_learner("APE_X")
+    out = {}
+    for tag, model, seed in (("online", l.model, 101), ("target", l.target_model, 202)):
+        sd = model.state_dict()
+        names = list(sd.keys())
+        ws = seeded_weights([tuple(sd[k].shape) for k in names], seed)
+        model.load_state_dict({k: torch.from_numpy(w) for k, w in zip(names, ws)})
+        out[f"{tag}_names"] = np.array(names)
+    rng = np.random.default_rng(0xB200 + 99)
+    s = rng.integers(0, 256, size=(B, 4, 84, 84), dtype=np.uint8)
+    ns = rng.integers(0, 256, size=(B, 4, 84, 84), dtype=np.uint8)
+    a = np.array([int(x) for x in rng.integers(0, 6, size=B)], dtype=object)
+    r = np.array([float(x) for x in np.clip(rng.standard_normal(B), -1, 1)], dtype=object)
+    d = np.array([bool(x) for x in (rng.random(B) < 0.25)], dtype=object)
+    w = torch.from_numpy(rng.uniform(0.2, 1.0, size=B).astype(np.float32))
+    info, prio, idx, mean_w = l.train([s, a, r, ns, d, w, torch.arange(B)])
+    out["new_priority"] = np.asarray(prio, np.float32)
+    out["mean_value"] = np.float32(info["mean_value"])
+    out["p_norm"] = np.float32(info["p_norm"])
+    for k, v in l.model.state_dict().items():
+        out["after_" + k] = v.reshape(-1)[:256].numpy().copy()
+    out["batch"] = np.int64(B)
+    np.savez_compressed(os.path.join(HERE, "apex_e2e.npz"), **out)
+    print("apex_e2e.npz:", len(out), "arrays")
+
+
+GROUPS = {"tree": gen_tree, "apex": gen_apex, "r2d2": gen_r2d2, "impala": gen_impala, "apex_e2e": gen_apex_e2e}
 
 if __name__ == "__main__":
     want = sys.argv[1:] or list(GROUPS)

@@ -265,3 +265,53 @@ def test_fused_rmsprop_matches_torch_optim(centered, eps, alpha):
         for p, q in zip(ref, mine):
             np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-6, atol=2e-8)
             assert float(q.grad.abs().max()) == 0.0            # zero_grad fused
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_learner_train_end_to_end_vs_reference_golden(apex, golden, fused):
+    """The whole reference Learner.train (run on the CPU by tests/golden/make_golden.py: 3 forwards,
+    double-DQN target, clipped TD, priority, IS-weighted loss, backward, centered RMSprop) against
+    distributed_rl_b200.apex.Learner.train on the GPU with the same seeded weights and minibatch.
+    `fused` routes conv_1 through the tcgen05 kernel via an in-replay batch and fused_step."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import seeded_weights
+    g = golden("apex_e2e")
+    B = int(g["batch"])
+    cfg = apex.ApexConfig(BATCHSIZE=B, REPLAY_MEMORY_LEN=64, BUFFER_SIZE=0, LEARNER_DEVICE="cuda:0",
+                          FUSED_CONV1=fused)
+    L = apex.Learner(cfg, connect=None, start_replay=False)
+    for model, seed, tag in ((L.model, 101, "online"), (L.target_model, 202, "target")):
+        names = [str(n) for n in g[f"{tag}_names"]]
+        sd = model.state_dict()
+        assert list(sd.keys()) == names                       # same state_dict key order as the reference
+        ws = seeded_weights([tuple(sd[k].shape) for k in names], seed)
+        model.load_state_dict({k: torch.from_numpy(w) for k, w in zip(names, ws)})
+    rng = np.random.default_rng(0xB200 + 99)                   # same draws as gen_apex_e2e
+    s = rng.integers(0, 256, size=(B, 4, 84, 84), dtype=np.uint8)
+    ns = rng.integers(0, 256, size=(B, 4, 84, 84), dtype=np.uint8)
+    a = np.array([int(x) for x in rng.integers(0, 6, size=B)], dtype=object)
+    r = np.array([float(x) for x in np.clip(rng.standard_normal(B), -1, 1)], dtype=object)
+    d = np.array([bool(x) for x in (rng.random(B) < 0.25)], dtype=object)
+    w = torch.from_numpy(rng.uniform(0.2, 1.0, size=B).astype(np.float32))
+    if not fused:
+        info, prio, idx, mean_w = L.train([s, a, r, ns, d, w, torch.arange(B)])
+        prio = prio.cpu().numpy(); mean_value = float(info["mean_value"]); p_norm = float(info["p_norm"])
+    else:
+        # put exactly this minibatch into the replay, sample it with explicit uniforms in order
+        st = L.memory.store
+        st.push([s, ns, a.astype(np.int32), r.astype(np.float32), d.astype(np.uint8)], np.ones(B, np.float32))
+        idx = torch.arange(B, device="cuda")
+        L._conv1_ready()
+        out = L._forward_backward_fused(idx, torch.from_numpy(a.astype(np.int64)).cuda(),
+                                        torch.from_numpy(r.astype(np.float32)).cuda(),
+                                        torch.from_numpy(d.astype(np.uint8)).cuda(), w.cuda())
+        info = L.step()
+        prio = out["prio"].cpu().numpy(); mean_value = float(out["scalars"][1]); p_norm = float(info["p_norm"])
+    np.testing.assert_allclose(prio, g["new_priority"], rtol=2e-4, atol=2e-5)     # Q-values through a CPU vs GPU net
+    np.testing.assert_allclose(mean_value, float(g["mean_value"]), atol=2e-5)
+    np.testing.assert_allclose(p_norm, float(g["p_norm"]), rtol=1e-3)
+    for k, v in L.model.state_dict().items():
+        got = v.reshape(-1)[:256].cpu().numpy() if v.is_contiguous() else v.contiguous().reshape(-1)[:256].cpu().numpy()
+        # centered RMSprop's first step is ~ lr*sign(g)/0.218: insensitive to |g|, so 1e-6 absolute
+        np.testing.assert_allclose(got, g["after_" + k], rtol=0, atol=2e-6, err_msg=k)
