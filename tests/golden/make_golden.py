@@ -383,7 +383,76 @@ def gen_apex_e2e():
     print("apex_e2e.npz:", len(out), "arrays")
 
 
-GROUPS = {"tree": gen_tree, "apex": gen_apex, "r2d2": gen_r2d2, "impala": gen_impala, "apex_e2e": gen_apex_e2e}
+def _load_seeded(model, seed):
+    import numpy as np
+    import torch
+    sd = model.state_dict()
+    names = list(sd.keys())
+    ws = seeded_weights([tuple(sd[k].shape) if sd[k].dim() > 1 else (sd[k].shape[0], 64) for k in names], seed)
+    fixed = {}
+    for k, w in zip(names, ws):
+        fixed[k] = torch.from_numpy(w if sd[k].dim() > 1 else np.ascontiguousarray(w[:, 0]))
+    model.load_state_dict(fixed)
+    return names
+
+
+def gen_r2d2_e2e():
+    """Whole reference R2D2 Learner.train on the CPU (burn-in, LSTM, targets, clip 40, Adam), MEM = T/2."""
+    import numpy as np
+    import torch
+    from oracle import ref_harness as H
+
+    T, MEM, B = 16, 8, 4
+    H.enter_reference("r2d2.json", {"FIXED_TRAJECTORY": T, "MEM": MEM, "BATCHSIZE": B})
+    l = H.bare_learner("R2D2")
+    out = {"online_names": np.array(_load_seeded(l.model, 303)), "target_names": np.array(_load_seeded(l.target_model, 404))}
+    rng = np.random.default_rng(0xB200 + 77)
+    s = rng.integers(0, 256, size=(B, T, 4, 84, 84), dtype=np.uint8)
+    a = rng.integers(0, 6, size=(B, T)).astype(np.int32)
+    r = rng.standard_normal((B, T)).astype(np.float32)
+    notdone = np.array([float(x) for x in (rng.random(B) > 0.3)])
+    w = torch.from_numpy(rng.uniform(0.2, 1.0, size=B).astype(np.float32))
+    h0 = torch.from_numpy((rng.standard_normal((1, B, 512)) * 0.1).astype(np.float32))
+    h1 = torch.from_numpy((rng.standard_normal((1, B, 512)) * 0.1).astype(np.float32))
+    info, prio, idx = l.train([(h0, h1), s, a, r, notdone, w, torch.arange(B)])
+    out["new_priority"] = np.asarray(prio, np.float32)
+    out["mean_value"] = np.float32(info["mean_value"])
+    out["p_norm"] = np.float32(info["p_norm"])
+    for k, v in l.model.state_dict().items():
+        out["after_" + k] = v.reshape(-1)[:256].numpy().copy()
+    out["dims"] = np.array([T, MEM, B], np.int64)
+    np.savez_compressed(os.path.join(HERE, "r2d2_e2e.npz"), **out)
+    print("r2d2_e2e.npz:", len(out), "arrays")
+
+
+def gen_impala_e2e():
+    """Whole reference IMPALA Learner.train on the CPU (V-trace, losses, clip 40, RMSprop)."""
+    import numpy as np
+    import torch
+    from oracle import ref_harness as H
+
+    B = 8
+    H.enter_reference("impala.json", {"BATCHSIZE": B})
+    import configuration as C  # type: ignore
+    T = C.UNROLL_STEP
+    l = H.bare_learner("IMPALA")
+    out = {"names": np.array(_load_seeded(l.model, 505))}
+    rng = np.random.default_rng(0xB200 + 55)
+    s = rng.integers(0, 256, size=(T + 1, B, 4 * 84 * 84), dtype=np.uint8)
+    a = rng.integers(0, 6, size=(T, B)).astype(np.int64)
+    mu = rng.uniform(0.05, 0.9, size=(T, B)).astype(np.float32)
+    r = rng.standard_normal((T, B)).astype(np.float32)
+    done = (rng.random(B) > 0.3).astype(np.float32)
+    l.train((s, a, mu, r, done), 0)
+    for k, v in l.model.state_dict().items():
+        out["after_" + k] = v.reshape(-1)[:256].numpy().copy()
+    out["dims"] = np.array([T, B], np.int64)
+    np.savez_compressed(os.path.join(HERE, "impala_e2e.npz"), **out)
+    print("impala_e2e.npz:", len(out), "arrays")
+
+
+GROUPS = {"tree": gen_tree, "apex": gen_apex, "r2d2": gen_r2d2, "impala": gen_impala, "apex_e2e": gen_apex_e2e,
+          "r2d2_e2e": gen_r2d2_e2e, "impala_e2e": gen_impala_e2e}
 
 if __name__ == "__main__":
     want = sys.argv[1:] or list(GROUPS)

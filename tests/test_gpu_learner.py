@@ -315,3 +315,72 @@ def test_learner_train_end_to_end_vs_reference_golden(apex, golden, fused):
         got = v.reshape(-1)[:256].cpu().numpy() if v.is_contiguous() else v.contiguous().reshape(-1)[:256].cpu().numpy()
         # centered RMSprop's first step is ~ lr*sign(g)/0.218: insensitive to |g|, so 1e-6 absolute
         np.testing.assert_allclose(got, g["after_" + k], rtol=0, atol=2e-6, err_msg=k)
+
+
+def _golden_tools():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden
+    return make_golden
+
+
+def test_r2d2_learner_train_end_to_end_vs_reference_golden(golden):
+    """Reference R2D2 Learner.train on the CPU (burn-in, LSTM, n-step targets with h / h^-1, clip 40,
+    Adam) vs distributed_rl_b200.r2d2.Learner.train on the GPU, seeded weights + sequences."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributed_rl_b200 import r2d2
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mg = _golden_tools()
+    g = golden("r2d2_e2e")
+    T, MEM, B = [int(x) for x in g["dims"]]
+    cfg = r2d2.R2D2Config(BATCHSIZE=B, FIXED_TRAJECTORY=T, MEM=MEM, REPLAY_MEMORY_LEN=16, BUFFER_SIZE=0)
+    L = r2d2.Learner(cfg)
+    assert mg._load_seeded(L.model, 303) == [str(n) for n in g["online_names"]]
+    assert mg._load_seeded(L.target_model, 404) == [str(n) for n in g["target_names"]]
+    L.model.cuda(); L.target_model.cuda()
+    rng = np.random.default_rng(0xB200 + 77)
+    s = rng.integers(0, 256, size=(B, T, 4, 84, 84), dtype=np.uint8)
+    a = rng.integers(0, 6, size=(B, T)).astype(np.int32)
+    r = rng.standard_normal((B, T)).astype(np.float32)
+    notdone = np.array([float(x) for x in (rng.random(B) > 0.3)])
+    w = torch.from_numpy(rng.uniform(0.2, 1.0, size=B).astype(np.float32))
+    h0 = torch.from_numpy((rng.standard_normal((1, B, 512)) * 0.1).astype(np.float32))
+    h1 = torch.from_numpy((rng.standard_normal((1, B, 512)) * 0.1).astype(np.float32))
+    info, prio, idx = L.train([(h0, h1), torch.from_numpy(s), torch.from_numpy(a), torch.from_numpy(r),
+                               torch.from_numpy(notdone.astype(np.float32)), w, torch.arange(B)])
+    np.testing.assert_allclose(prio.cpu().numpy(), g["new_priority"], rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(float(info["mean_value"]), float(g["mean_value"]), atol=5e-5)
+    np.testing.assert_allclose(float(info["p_norm"]), float(g["p_norm"]), rtol=2e-3)
+    for k, v in L.model.state_dict().items():
+        np.testing.assert_allclose(v.contiguous().reshape(-1)[:256].cpu().numpy(), g["after_" + k], rtol=0, atol=5e-6,
+                                   err_msg=k)
+
+
+def test_impala_learner_train_end_to_end_vs_reference_golden(golden):
+    """Reference IMPALA Learner.train on the CPU (V-trace, actor/critic/entropy loss, clip 40, RMSprop)
+    vs distributed_rl_b200.impala.Learner.train on the GPU."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributed_rl_b200 import impala
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mg = _golden_tools()
+    g = golden("impala_e2e")
+    T, B = [int(x) for x in g["dims"]]
+    cfg = impala.ImpalaConfig(BATCHSIZE=B, UNROLL_STEP=T, REPLAY_MEMORY_LEN=16, BUFFER_SIZE=0)
+    L = impala.Learner(cfg)
+    assert mg._load_seeded(L.model, 505) == [str(n) for n in g["names"]]
+    L.model.cuda()
+    rng = np.random.default_rng(0xB200 + 55)
+    s = rng.integers(0, 256, size=(T + 1, B, 4 * 84 * 84), dtype=np.uint8)
+    a = rng.integers(0, 6, size=(T, B)).astype(np.int64)
+    mu = rng.uniform(0.05, 0.9, size=(T, B)).astype(np.float32)
+    r = rng.standard_normal((T, B)).astype(np.float32)
+    done = (rng.random(B) > 0.3).astype(np.float32)
+    L.train((s, a, mu, r, done), 0)
+    for k, v in L.model.state_dict().items():
+        # RMSprop (lr 6e-4, eps 1e-5): first step ~ lr * g / (0.1|g| + eps), so compare to 1e-5 absolute
+        np.testing.assert_allclose(v.contiguous().reshape(-1)[:256].cpu().numpy(), g["after_" + k], rtol=0, atol=1e-5,
+                                   err_msg=k)
