@@ -42,8 +42,6 @@ k_apex_target(const float* __restrict__ q_s, const float* __restrict__ qn_on,
               float* __restrict__ grad_q, float* __restrict__ scalars) {
   __shared__ double s_buf[APEX_THREADS / 32];
   double acc_loss = 0.0, acc_y = 0.0, acc_w = 0.0;
-  const float invB = 1.0f;  // divisions by B are done explicitly below
-  (void)invB;
   for (int b = threadIdx.x; b < B; b += APEX_THREADS) {
     const float* qo = qn_on + (int64_t)b * A;
     int a_star = 0;
@@ -198,7 +196,6 @@ __global__ void k_r2d2_finish(const double* __restrict__ partial, int B, int Lm1
 // (T, B) so a warp's loads at step t are one coalesced 128-byte line.
 // ----------------------------------------------------------------------------
 constexpr int VTRACE_THREADS = 128;
-constexpr int VTRACE_MAX_T = 256;
 
 __global__ void __launch_bounds__(VTRACE_THREADS)
 k_vtrace(const float* __restrict__ pi_a, const float* __restrict__ mu_a, const float* __restrict__ value,

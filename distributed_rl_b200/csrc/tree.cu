@@ -142,7 +142,6 @@ k_tree_sample(const TreeNode* __restrict__ node, int64_t cap2,
   }
 }
 
-__global__ void k_rng_advance(uint64_t* __restrict__ rng_state, uint64_t n) { rng_state[1] += n; }
 __global__ void k_rng_seed(uint64_t* __restrict__ rng_state, uint64_t seed, uint64_t ctr) {
   rng_state[0] = seed; rng_state[1] = ctr; rng_state[2] = 0;
 }
