@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="keep the network in NCHW (default: channels_last)")
     ap.add_argument("--unfused-conv1", action="store_true", help="stage the batch and let cuDNN run conv_1")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.RMSprop instead of the fused kernel")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true", help="leave cuDNN's algorithm choice to its heuristics")
+    ap.add_argument("--blaslt", action="store_true", help="route fp32 GEMMs through cuBLASLt")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=48)
     return ap.parse_args()
@@ -201,6 +203,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # library knobs for the PyTorch remainder of the network (no precision change: fp32 matmul, TF32 conv)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
+    if args.blaslt:
+        torch.backends.cuda.preferred_blas_library("cublaslt")
     if world > 1:
         os.environ.pop("NCCL_DEBUG", None)      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
