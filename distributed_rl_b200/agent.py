@@ -93,6 +93,13 @@ class DenseStack(nn.Sequential):
             x = layer(x)
         return x
 
+    def forward_after_first(self, h):
+        """Continue after the first Linear (its output `h` was computed jointly with sibling heads)."""
+        x = h
+        for layer in list(self.children())[1:]:
+            x = layer(x)
+        return x
+
 
 class Recurrent(nn.Module):
     """netCat LSTMNET: single-layer LSTM that carries its cell state between calls."""
@@ -179,13 +186,35 @@ class GraphAgent(nn.Module):
             self._prev[name] = list(d.get("prevNodeNames", []))
             if kind == "LSTMNET":
                 self._recurrent.append(name)
+        # Sibling MLP heads fed by the same node (the dueling adv/val heads): their first Linear layers
+        # share the input, so they run as ONE GEMM on the concatenated weights (same maths, wider N).
+        self.fuse_sibling_heads = True
+        groups = {}
+        for name in order:
+            m = getattr(self, name)
+            if isinstance(m, DenseStack) and not self._ext[name] and len(self._prev[name]) == 1:
+                first = next(iter(m.children()))
+                if isinstance(first, nn.Linear) and first.bias is None:
+                    groups.setdefault((self._prev[name][0], first.in_features), []).append(name)
+        self._head_groups = {n: tuple(g) for g in groups.values() if len(g) > 1 for n in g}
 
     # -- execution: external inputs first, then upstream outputs (reference order) --
     def forward(self, inputs, preset: dict | None = None):
         """`preset` maps node names to already-computed outputs (used by the fused conv_1 path)."""
         vals = dict(preset) if preset else {}
+        first_out = {}
         for name in self._order:
             if name in vals:
+                continue
+            group = self._head_groups.get(name) if self.fuse_sibling_heads else None
+            if group is not None:
+                if name not in first_out:
+                    x = vals[self._prev[name][0]]
+                    ws = [next(iter(getattr(self, n).children())).weight for n in group]
+                    h = torch.nn.functional.linear(x, torch.cat(ws, 0))
+                    for n, part in zip(group, torch.split(h, [w.shape[0] for w in ws], dim=-1)):
+                        first_out[n] = part
+                vals[name] = getattr(self, name).forward_after_first(first_out[name])
                 continue
             srcs = [inputs[i] for i in self._ext[name]] + [vals[p] for p in self._prev[name]]
             vals[name] = getattr(self, name)(tuple(srcs))

@@ -52,6 +52,7 @@ class ApexConfig:
     CHANNELS_LAST: bool = True      # NHWC activations/weights: cuDNN's TF32 kernels skip their layout transposes
     FUSED_CONV1: bool = True        # gather + conv_1 on the tcgen05 tensor cores (csrc/conv1.cu) in fused_step
     FUSED_OPTIM: bool = True        # RMSprop + zero_grad + grad-norm in one launch (csrc/optim.cu)
+    CUDNN_BENCHMARK: bool = True    # let cuDNN time its conv_2/conv_3 algorithms once (no precision change)
 
     @staticmethod
     def from_configuration():
@@ -240,6 +241,8 @@ class Learner:
                  writer=None):
         self.cfg = cfg or ApexConfig.from_configuration()
         self.device = torch.device(self.cfg.LEARNER_DEVICE)
+        if self.cfg.CUDNN_BENCHMARK and self.device.type == "cuda":
+            torch.backends.cudnn.benchmark = True
         self.build_model()
         self.build_optim()
         self.connect = connect
