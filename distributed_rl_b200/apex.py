@@ -437,6 +437,10 @@ class Learner:
             self.connect.set("count", pickle.dumps(1))
             self.connect.set("target_state_dict", pickle.dumps(self.target_state_dict))
             self.connect.set("Start", pickle.dumps(True))
+        from .publish import ParamPublisher
+        pub = ParamPublisher(self.model, self.connect, "state_dict", "count")
+        pub_t = ParamPublisher(self.target_model, self.connect, "target_state_dict", None)
+        self._publishers = (pub, pub_t)
         step = 0
         t0 = time.time()
         acc = None
@@ -446,11 +450,10 @@ class Learner:
             acc = out["scalars"].clone() if acc is None else acc + out["scalars"]
             if step % self.cfg.TARGET_FREQUENCY == 0:
                 self.target_model.updateParameter(self.model, 1)
-                if self.connect is not None:
-                    self.connect.set("target_state_dict", pickle.dumps(self.target_state_dict))
-            if step % 50 == 0 and self.connect is not None:
-                self.connect.set("state_dict", pickle.dumps(self.state_dict))
-                self.connect.set("count", pickle.dumps(step - 50))
+                pub_t.snapshot(step)                 # async D2H; published by a later poll()
+            if step % 50 == 0:
+                pub.snapshot(step - 50)              # :212-216, without stalling the learner stream
+            pub.poll(); pub_t.poll()
             if step % log_every == 0:
                 loss, mean_value, mean_w = (acc / log_every).tolist()
                 dt = (time.time() - t0) / log_every

@@ -384,3 +384,32 @@ def test_impala_learner_train_end_to_end_vs_reference_golden(golden):
         # RMSprop (lr 6e-4, eps 1e-5): first step ~ lr * g / (0.1|g| + eps), so compare to 1e-5 absolute
         np.testing.assert_allclose(v.contiguous().reshape(-1)[:256].cpu().numpy(), g["after_" + k], rtol=0, atol=1e-5,
                                    err_msg=k)
+
+
+def test_async_parameter_publication_and_run_loop(apex):
+    """Learner.run publishes `state_dict` / `count` / `target_state_dict` under the reference's Redis
+    keys (APE_X/Learner.py:149-155,207-216) through the async publisher; payload = dict of CPU tensors
+    with the reference's key names, equal to the weights at the snapshot step."""
+    import pickle
+    from oracle.ref_harness import _StrictRedis
+    from distributed_rl_b200.publish import ParamPublisher
+    cfg = apex.ApexConfig(BATCHSIZE=32, REPLAY_MEMORY_LEN=4096, BUFFER_SIZE=0, TARGET_FREQUENCY=60,
+                          LEARNER_DEVICE="cuda:0")
+    conn = _StrictRedis()
+    L = apex.Learner(cfg, connect=conn, start_replay=False)
+    _fill(L, 4096)
+    # publisher alone: snapshot -> poll(block) reproduces the weights bit-exactly
+    pub = ParamPublisher(L.model, conn, "state_dict", "count")
+    pub.snapshot(7)
+    assert pub.poll(block=True)
+    sd = pickle.loads(conn.get("state_dict"))
+    assert pickle.loads(conn.get("count")) == 7
+    for k, v in L.model.state_dict().items():
+        assert torch.equal(sd[k], v.cpu())
+    steps = L.run(max_steps=120, log_every=10 ** 9)
+    assert steps == 120
+    for p in L._publishers:
+        p.poll(block=True)
+    assert L._publishers[0].published >= 1 and L._publishers[1].published >= 1
+    assert set(pickle.loads(conn.get("target_state_dict"))) == set(L.model.state_dict())
+    assert pickle.loads(conn.get("count")) in (0, 50)
