@@ -215,23 +215,32 @@ class Replay(threading.Thread):
 
 
 class _Conv1Gathered(torch.autograd.Function):
-    """conv_1 over replay rows `idx` of the `state` field.  Forward: fused gather+conv (tensor
-    cores, no staging).  Backward: only dL/dW is needed (the input is data); it is computed by
-    cuDNN from a gathered copy of the same rows — the one place the sampled s is staged."""
+    """conv_1 over rows `idx` of a uint8 frame table (a replay field or an explicit batch).
+    Forward: fused gather+conv on the tensor cores (or a precomputed output of the same kernel).
+    Backward: only dL/dW is needed (the input is data); cuDNN computes it from a gathered fp32
+    copy of the same rows — the one place the sampled frames are staged."""
 
     @staticmethod
-    def forward(ctx, weight, store, idx, pack, mem_format):
-        ctx.store, ctx.mem_format, ctx.wshape = store, mem_format, weight.shape
-        ctx.save_for_backward(idx)
-        return R.conv1_fused(store.field_view("state"), idx, pack, relu=False)[0]
+    def forward(ctx, weight, frames, idx, pack, mem_format, store=None, y_pre=None):
+        ctx.frames, ctx.store, ctx.mem_format, ctx.wshape = frames, store, mem_format, weight.shape
+        ctx.has_idx = idx is not None
+        ctx.save_for_backward(idx if idx is not None else torch.empty(0, dtype=torch.int64, device=frames.device))
+        if y_pre is not None:
+            return y_pre.view_as(y_pre)
+        return R.conv1_fused(frames, idx, pack, relu=False)[0]
 
     @staticmethod
     def backward(ctx, gy):
         (idx,) = ctx.saved_tensors
-        x = ctx.store.gather(idx, ctx.store.alloc_batch(idx.numel(), ("state",)))["state"]
+        if not ctx.has_idx:
+            x = ctx.frames
+        elif ctx.store is not None:    # TMA bulk gather straight from the replay payload
+            x = ctx.store.gather(idx, ctx.store.alloc_batch(idx.numel(), ("state",)))["state"]
+        else:
+            x = ctx.frames.index_select(0, idx)
         xf = (x.to(torch.float32) / 255.0).contiguous(memory_format=ctx.mem_format)
-        gw = torch.nn.grad.conv2d_weight(xf, ctx.wshape, gy, stride=4)
-        return gw, None, None, None, None
+        gw = torch.nn.grad.conv2d_weight(xf, ctx.wshape, gy.contiguous(memory_format=ctx.mem_format), stride=4)
+        return gw, None, None, None, None, None, None
 
 
 class Learner:
@@ -356,7 +365,7 @@ class Learner:
             y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
             qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
             qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
-        y = _Conv1Gathered.apply(w_on, st, idx, self._pack1, self._mf)
+        y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
         q = self.model.forward_from_conv1(y, False)[0]                       # :78
         notdone = 1.0 - done.to(torch.float32)
         out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,

@@ -18,7 +18,7 @@ import torch
 
 from . import replay as R
 from .agent import GraphAgent
-from .apex import make_optimizer, _MemoryView
+from .apex import make_optimizer, _MemoryView, _Conv1Gathered
 
 
 def default_r2d2_model() -> dict:
@@ -59,6 +59,7 @@ class R2D2Config:
     REDIS_SERVER: str = "localhost"
     OPTIM_INFO: dict = field(default_factory=lambda: {"name": "adam", "lr": 1e-4, "eps": 0.001})
     MODEL: dict = field(default_factory=default_r2d2_model)
+    FUSED_CONV1: bool = True     # conv_1 of every frame through libb2rl's tcgen05 kernel (gather fused)
 
     @staticmethod
     def from_configuration():
@@ -130,20 +131,25 @@ class Learner:
         h0, h1 = h0.to(dev), h1.to(dev)
         self.model.setCellState((h0, h1))                       # :86-87
         self.target_model.setCellState((h0, h1))
-        state = torch.as_tensor(state).to(dev).float() / 255.0  # :89-90
-        sv = state.permute(1, 0, 2, 3, 4).contiguous()          # time-major, :93
-        burn = sv[:MEM].reshape(-1, 4, 84, 84)
-        window = sv[MEM:].reshape(-1, 4, 84, 84)
-        with torch.no_grad():                                   # burn-in, :99-104
-            shape = torch.tensor([MEM, B, -1])
-            self.model.forward([burn, shape])
-            self.target_model.forward([burn, shape])
-            self.model.detachCellState()
-            self.target_model.detachCellState()
-        shape = torch.tensor([L, B, -1])
-        q = self.model.forward([window, shape])[0].view(L, B, A)              # :121
-        with torch.no_grad():
-            q_target = self.target_model.forward([window, shape])[0].view(L, B, A)   # :132
+        state = torch.as_tensor(state).to(dev)
+        fused = c.FUSED_CONV1 and state.dtype == torch.uint8 and self.model.first_conv_node() is not None
+        if fused:
+            q, q_target = self._forward_fused(state.contiguous(), T, MEM, B, A)
+        else:
+            state = state.float() / 255.0                       # :89-90
+            sv = state.permute(1, 0, 2, 3, 4).contiguous()      # time-major, :93
+            burn = sv[:MEM].reshape(-1, 4, 84, 84)
+            window = sv[MEM:].reshape(-1, 4, 84, 84)
+            with torch.no_grad():                               # burn-in, :99-104
+                shape = torch.tensor([MEM, B, -1])
+                self.model.forward([burn, shape])
+                self.target_model.forward([burn, shape])
+                self.model.detachCellState()
+                self.target_model.detachCellState()
+            shape = torch.tensor([L, B, -1])
+            q = self.model.forward([window, shape])[0].view(L, B, A)              # :121
+            with torch.no_grad():
+                q_target = self.target_model.forward([window, shape])[0].view(L, B, A)   # :132
         act = torch.as_tensor(action).to(dev, torch.int64).t()[MEM:-1].contiguous()      # (L-1, B)
         rew = torch.as_tensor(reward).to(dev, torch.float32).t()[MEM:-1].contiguous()
         nd = torch.as_tensor(notdone).to(dev, torch.float32).contiguous()
@@ -154,6 +160,39 @@ class Learner:
         info["mean_value"] = out["scalars"][1]
         info["loss"] = out["scalars"][0]
         return info, out["prio"], idx
+
+    def _forward_fused(self, state_u8, T, MEM, B, A):
+        """Same forward passes with conv_1 on the tensor cores: the (b, t) -> time-major reordering and
+        the uint8 -> /255 conversion are folded into the kernel's gather (row index = b*T + t)."""
+        dev = self.device
+        if not hasattr(self, "_pack2"):
+            self._pack2 = R.Conv1Pack(2, dev)
+            self._pack1 = R.Conv1Pack(1, dev)
+            self._conv_name = self.model.first_conv_node()
+            t_idx = torch.arange(T, device=dev).view(T, 1)
+            b_idx = torch.arange(B, device=dev).view(1, B)
+            self._tm_rows = (b_idx * T + t_idx).reshape(-1).contiguous()      # time-major list of (b, t) rows
+        frames = state_u8.view(B * T, 4, 84, 84)
+        w_on = getattr(self.model, self._conv_name).conv_1.weight
+        w_tg = getattr(self.target_model, self._conv_name).conv_1.weight
+        self._pack2.pack(0, w_on); self._pack2.pack(1, w_tg); self._pack1.pack(0, w_on)
+        rows_burn, rows_win = self._tm_rows[:MEM * B], self._tm_rows[MEM * B:]
+        L = T - MEM
+        with torch.no_grad():                                   # burn-in, :99-104
+            y_on, y_tg = R.conv1_fused(frames, rows_burn, self._pack2, relu=True)
+            shape = torch.tensor([MEM, B, -1])
+            self.model.forward_from_conv1(y_on, True, [shape])
+            self.target_model.forward_from_conv1(y_tg, True, [shape])
+            self.model.detachCellState()
+            self.target_model.detachCellState()
+            y_on_w, y_tg_w = R.conv1_fused(frames, rows_win, self._pack2, relu=False)
+        shape = torch.tensor([L, B, -1])
+        mf = torch.contiguous_format
+        y = _Conv1Gathered.apply(w_on, frames, rows_win, self._pack1, mf, None, y_on_w)
+        q = self.model.forward_from_conv1(y, False, [shape])[0].view(L, B, A)             # :121
+        with torch.no_grad():
+            q_target = self.target_model.forward_from_conv1(torch.relu(y_tg_w), True, [shape])[0].view(L, B, A)
+        return q, q_target
 
     def step(self):
         """R2D2/Learner.py:200-215: norm, clip at 40, Adam."""
