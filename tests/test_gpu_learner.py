@@ -145,11 +145,11 @@ def test_r2d2_learner_train_matches_oracle_and_autograd():
     cap = {}
     om, ot = L.model.forward, L.target_model.forward
 
-    def fm(x):
-        o = om(x); cap.setdefault("q", []).append(o[0]); return o
+    def fm(x, **kw):
+        o = om(x, **kw); cap.setdefault("q", []).append(o[0]); return o
 
-    def ft(x):
-        o = ot(x); cap.setdefault("qt", []).append(o[0]); return o
+    def ft(x, **kw):
+        o = ot(x, **kw); cap.setdefault("qt", []).append(o[0]); return o
 
     L.model.forward, L.target_model.forward = fm, ft
     info, prio, idx2 = L.train(batch)
