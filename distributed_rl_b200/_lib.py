@@ -44,8 +44,8 @@ SIGNATURES = {
     "b2rl_r2d2_target": (C.c_int, [c_vp] * 6 + [c_i32, c_i32, c_i32, c_i32, c_f64, c_f32, c_i32]
                          + [c_vp] * 6),
     "b2rl_vtrace": (C.c_int, [c_vp] * 5 + [c_i32, c_i32, c_f32, c_f32, c_f32, c_f32] + [c_vp] * 3),
-    "b2rl_conv1_pack": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
-    "b2rl_conv1_fused": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    "b2rl_conv1_pack": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "b2rl_conv1_fused": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),
     "b2rl_rmsprop_step": (C.c_int, [C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                     C.POINTER(c_i64), c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp]),
     "b2rl_launch_count": (c_i64, []),

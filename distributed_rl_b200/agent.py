@@ -55,14 +55,14 @@ class ConvStack(nn.Sequential):
         return x
 
     def is_atari_conv1(self) -> bool:
-        """True if the first layer is the 8x8/stride-4, 4->32, bias-free conv followed by ReLU that
-        libb2rl's fused gather+conv1 kernel implements (cfg/ape_x.json, cfg/r2d2.json)."""
+        """True if the first layer is the 8x8/stride-4, 4->32 (or 4->16), bias-free conv followed by ReLU
+        that libb2rl's fused gather+conv1 kernel implements (cfg/ape_x.json, cfg/r2d2.json, cfg/impala.json)."""
         layers = list(self.children())
         if len(layers) < 2 or not isinstance(layers[0], nn.Conv2d) or not isinstance(layers[1], nn.ReLU):
             return False
         c = layers[0]
-        return (c.in_channels, c.out_channels, c.kernel_size, c.stride, c.padding, c.bias) == \
-            (4, 32, (8, 8), (4, 4), (0, 0), None)
+        return (c.in_channels, c.kernel_size, c.stride, c.padding, c.bias) == (4, (8, 8), (4, 4), (0, 0), None) \
+            and c.out_channels in (16, 32)
 
     def forward_tail(self, y, relu_applied: bool):
         """Continue after conv_1: `y` is conv_1's output (pre- or post-ReLU)."""

@@ -347,9 +347,10 @@ class Learner:
         if not self.cfg.FUSED_CONV1 or self.model.first_conv_node() is None:
             return False
         if not hasattr(self, "_pack2"):
-            self._pack1 = R.Conv1Pack(1, self.device)     # online net (grad pass on s)
-            self._pack2 = R.Conv1Pack(2, self.device)     # online + target in one pass over s'
             self._conv_name = self.model.first_conv_node()
+            c_out = getattr(self.model, self._conv_name).conv_1.out_channels
+            self._pack1 = R.Conv1Pack(1, self.device, c_out)     # online net (grad pass on s)
+            self._pack2 = R.Conv1Pack(2, self.device, c_out)     # online + target in one pass over s'
         return True
 
     def _forward_backward_fused(self, idx, action, reward, done, weight):

@@ -37,14 +37,14 @@
 namespace b2rl {
 namespace conv1 {
 
-constexpr int C_IN = 4, HW = 84, KS = 8, STRIDE = 4, OHW = 20, C_OUT = 32;
+constexpr int C_IN = 4, HW = 84, KS = 8, STRIDE = 4, OHW = 20;
+constexpr int C_OUT_MAX = 32;                      // output channels: 32 (Ape-X / R2D2) or 16 (IMPALA), a template parameter
 constexpr int K_TOTAL = C_IN * KS * KS;            // 256
 constexpr int FRAME_BYTES = C_IN * HW * HW;        // 28 224
 constexpr int POS = OHW * OHW;                     // 400 output positions per frame stack
 constexpr int TILE_M = 128;
 constexpr int TILES = (POS + TILE_M - 1) / TILE_M; // 4 (the last one has 16 valid rows)
 constexpr int NSPLIT = 4;
-constexpr int N_PER_NET = NSPLIT * C_OUT;          // 128 MMA columns per network
 constexpr int A_STAGES = 2;
 constexpr int STAGE_OUT_BYTES = 8 * 32 * 128;      // epilogue staging: 8 warps x 32 rows x 128 B
 constexpr int A_TILE_BYTES = TILE_M * K_TOTAL;     // 32 768: 2 K-chunks x 128 rows x 128 B
@@ -123,7 +123,8 @@ __host__ __device__ __forceinline__ int sw128_offset(int rows, int n, int k) {
 
 // ---- weight packing: fp32 [32][256] -> 4 signed 7-bit digits per weight, per-channel scale ----
 __global__ void __launch_bounds__(K_TOTAL)
-k_conv1_pack(const float* __restrict__ w, int net, int n_nets, int8_t* __restrict__ bq, float* __restrict__ scale) {
+k_conv1_pack(const float* __restrict__ w, int net, int n_nets, int c_out, int8_t* __restrict__ bq,
+             float* __restrict__ scale) {
   __shared__ float s_max[K_TOTAL / 32];
   const int co = blockIdx.x, k = threadIdx.x;
   const float v = w[co * K_TOTAL + k];
@@ -135,14 +136,14 @@ k_conv1_pack(const float* __restrict__ w, int net, int n_nets, int8_t* __restric
   m = s_max[0];
   for (int i = 1; i < K_TOTAL / 32; ++i) m = fmaxf(m, s_max[i]);
   const float s = (m > 0.0f) ? m / 127.0f : 1.0f;
-  if (k == 0) scale[net * C_OUT + co] = s / 255.0f;   // the /255 of the input normalisation is folded in
+  if (k == 0) scale[net * c_out + co] = s / 255.0f;   // the /255 of the input normalisation is folded in
   double x = (double)v / (double)s;
-  const int rows = n_nets * N_PER_NET;
+  const int rows = n_nets * NSPLIT * c_out;
 #pragma unroll
   for (int j = 0; j < NSPLIT; ++j) {
     double q = rint(x);
     q = fmin(fmax(q, -127.0), 127.0);
-    bq[sw128_offset(rows, net * N_PER_NET + j * C_OUT + co, k)] = (int8_t)q;
+    bq[sw128_offset(rows, net * NSPLIT * c_out + j * c_out + co, k)] = (int8_t)q;
     x = (x - q) * 128.0;
   }
 }
@@ -159,10 +160,12 @@ struct Params {
   long long* dbg;            // optional [gridDim.x][16] cycle counters (B2RL_CONV1_DBG=1), else nullptr
 };
 
-template <int N_NETS>
+template <int N_NETS, int C_OUT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_conv1_fused(const __grid_constant__ Params P) {
-  constexpr int N_TOTAL = N_NETS * N_PER_NET;          // MMA N: 128 or 256
+  constexpr int N_PER_NET = NSPLIT * C_OUT;            // MMA columns per network: 128 (64 for 16 channels)
+  constexpr int N_TOTAL = N_NETS * N_PER_NET;          // MMA N: 64 .. 256
+  constexpr int ROW_BYTES = C_OUT * 4;                 // one output position of one network
   constexpr int B_BYTES = N_TOTAL * K_TOTAL;           // 32 / 64 KiB
   constexpr uint32_t TMEM_COLS = 2 * N_TOTAL;          // double-buffered accumulator
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -175,7 +178,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
   __shared__ __align__(8) uint64_t b_full, raw_full[2], raw_empty[2], a_full[A_STAGES], a_empty[A_STAGES],
       t_full[2], t_empty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_scale[2 * C_OUT];
+  __shared__ float s_scale[2 * C_OUT_MAX];
   if (threadIdx.x < N_NETS * C_OUT) s_scale[threadIdx.x] = P.scale[threadIdx.x] * (1.0f / 128.0f);   // exact
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,7 +205,8 @@ k_conv1_fused(const __grid_constant__ Params P) {
     // ------------------------------ TMA loader ------------------------------
     if (lane == 0) {
       mbar_expect_tx(&b_full, B_BYTES);
-      for (int off = 0; off < B_BYTES; off += 32768) bulk_g2s(sB + off, P.bq + off, 32768, &b_full);
+      constexpr int LOAD_CHUNK = (B_BYTES < 32768) ? B_BYTES : 32768;
+      for (int off = 0; off < B_BYTES; off += LOAD_CHUNK) bulk_g2s(sB + off, P.bq + off, LOAD_CHUNK, &b_full);
       int it = 0;
       for (int64_t k = first; k < P.n; k += stride, ++it) {
         const int s = it & 1;
@@ -321,7 +325,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
           const int net = (N_NETS == 2) ? eg : 0;
           const bool active = (N_NETS == 2) || eg == 0;   // one network: group 0 does it all (full-line stores)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < C_OUT / 16; ++h) {
             if (!active) break;
             int32_t q0[16], q1[16], q2[16], q3[16];
             const uint32_t col = tbase + net * N_PER_NET + h * 16;
@@ -353,13 +357,13 @@ k_conv1_fused(const __grid_constant__ Params P) {
             }
           }
           __syncwarp();
-          // the warp's 32 rows are 4 KiB contiguous in the NHWC output: 8 fully coalesced 512-byte stores
+          // the warp's 32 rows are contiguous in the NHWC output (4 KiB at 32 channels): coalesced 512-byte stores
           if (rows_valid > 0) {
             float* obase = P.out + (((int64_t)net * P.n + k) * POS + (t * TILE_M + wq * 32)) * C_OUT;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int off = (i * 32 + lane) * 16;          // byte offset inside the 4 KiB block
-              const int row = off >> 7, unit = (off >> 4) & 7;
+            for (int i = 0; i < ROW_BYTES / 16; ++i) {
+              const int off = (i * 32 + lane) * 16;          // byte offset inside the warp's contiguous block
+              const int row = off / ROW_BYTES, unit = (off % ROW_BYTES) >> 4;
               if (row < rows_valid && active) {
                 const float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
                 *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(obase) + off) = v;
@@ -384,9 +388,9 @@ k_conv1_fused(const __grid_constant__ Params P) {
   }
 }
 
-template <int N_NETS>
+template <int N_NETS, int C_OUT>
 constexpr size_t smem_bytes() {
-  return (size_t)N_NETS * N_PER_NET * K_TOTAL + (size_t)A_STAGES * A_TILE_BYTES + 2 * (size_t)RAW_STRIDE +
+  return (size_t)N_NETS * NSPLIT * C_OUT * K_TOTAL + (size_t)A_STAGES * A_TILE_BYTES + 2 * (size_t)RAW_STRIDE +
          (size_t)STAGE_OUT_BYTES + 1024;
 }
 
@@ -395,48 +399,59 @@ constexpr size_t smem_bytes() {
 
 using namespace b2rl;
 
-extern "C" int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, int8_t* bq_out_dev,
+extern "C" int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, int32_t c_out, int8_t* bq_out_dev,
                                float* scale_out_dev, void* stream) {
   B2RL_REQUIRE(w_dev && bq_out_dev && scale_out_dev, "null argument");
   B2RL_REQUIRE(n_nets >= 1 && n_nets <= 2 && net >= 0 && net < n_nets, "n_nets must be 1 or 2");
-  conv1::k_conv1_pack<<<conv1::C_OUT, conv1::K_TOTAL, 0, (cudaStream_t)stream>>>(w_dev, net, n_nets, bq_out_dev,
-                                                                                scale_out_dev);
+  B2RL_REQUIRE(c_out == 16 || c_out == 32, "c_out must be 16 or 32");
+  conv1::k_conv1_pack<<<c_out, conv1::K_TOTAL, 0, (cudaStream_t)stream>>>(w_dev, net, n_nets, c_out, bq_out_dev,
+                                                                         scale_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
 }
 
+template <int N_NETS, int C_OUT>
+static cudaError_t conv1_launch(const conv1::Params& P, unsigned grid, cudaStream_t st) {
+  static bool attr[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr[dev & 63]) {
+    e = cudaFuncSetAttribute(conv1::k_conv1_fused<N_NETS, C_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)conv1::smem_bytes<N_NETS, C_OUT>());
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  conv1::k_conv1_fused<N_NETS, C_OUT><<<grid, conv1::THREADS, conv1::smem_bytes<N_NETS, C_OUT>(), st>>>(P);
+  return cudaSuccess;
+}
+
 extern "C" int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
-                                const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, float* out_dev,
-                                int32_t relu, void* stream) {
+                                const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, int32_t c_out,
+                                float* out_dev, int32_t relu, void* stream) {
   B2RL_REQUIRE(n >= 0, "negative n");
   if (n == 0) return B2RL_OK;
   B2RL_REQUIRE(frames_dev && bq_dev && scale_dev && out_dev, "null argument");
   B2RL_REQUIRE(n_nets == 1 || n_nets == 2, "n_nets must be 1 or 2");
+  B2RL_REQUIRE(c_out == 16 || c_out == 32, "c_out must be 16 or 32");
   B2RL_REQUIRE(capacity >= 1, "capacity must be positive");
   B2RL_REQUIRE(((uintptr_t)frames_dev % 16 == 0) && ((uintptr_t)bq_dev % 16 == 0) && ((uintptr_t)out_dev % 16 == 0),
                "frames, packed weights and output must be 16-byte aligned");
   int dev = 0;
   B2RL_CUDA(cudaGetDevice(&dev));
   static int sms[64] = {0};
-  static bool init[64] = {false};
-  if (!init[dev & 63]) {
-    B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-    B2RL_CUDA(cudaFuncSetAttribute(conv1::k_conv1_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)conv1::smem_bytes<1>()));
-    B2RL_CUDA(cudaFuncSetAttribute(conv1::k_conv1_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)conv1::smem_bytes<2>()));
-    init[dev & 63] = true;
-  }
+  if (!sms[dev & 63]) B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
   static long long* dbg_buf = nullptr;
   if (getenv("B2RL_CONV1_DBG") && !dbg_buf) B2RL_CUDA(cudaMalloc(&dbg_buf, 256 * 16 * sizeof(long long)));
   if (dbg_buf) B2RL_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * 16 * sizeof(long long), (cudaStream_t)stream));
   conv1::Params P{frames_dev, idx_dev, n, capacity, bq_dev, scale_dev, out_dev, relu, dbg_buf};
   const unsigned grid = (unsigned)((n < sms[dev & 63]) ? n : sms[dev & 63]);
-  if (n_nets == 1)
-    conv1::k_conv1_fused<1><<<grid, conv1::THREADS, conv1::smem_bytes<1>(), (cudaStream_t)stream>>>(P);
-  else
-    conv1::k_conv1_fused<2><<<grid, conv1::THREADS, conv1::smem_bytes<2>(), (cudaStream_t)stream>>>(P);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (c_out == 32) e = (n_nets == 1) ? conv1_launch<1, 32>(P, grid, st) : conv1_launch<2, 32>(P, grid, st);
+  else             e = (n_nets == 1) ? conv1_launch<1, 16>(P, grid, st) : conv1_launch<2, 16>(P, grid, st);
+  B2RL_CUDA(e);
   count_launch();
   B2RL_CHECK_LAUNCH();
   if (dbg_buf) {   // profiling aid: per-role cycle counters of CTA 0 (synchronous; never set in production)

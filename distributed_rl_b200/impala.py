@@ -13,7 +13,7 @@ import torch
 
 from . import replay as R
 from .agent import GraphAgent
-from .apex import make_optimizer
+from .apex import make_optimizer, _Conv1Gathered
 
 
 def default_impala_model() -> dict:
@@ -43,6 +43,7 @@ class ImpalaConfig:
     REDIS_SERVER: str = "localhost"
     OPTIM_INFO: dict = field(default_factory=lambda: {"name": "rmsprop", "lr": 6e-4, "decay": 0})
     MODEL: dict = field(default_factory=default_impala_model)
+    FUSED_CONV1: bool = True     # conv_1 (4 -> 16 channels) of every frame through libb2rl's tcgen05 kernel
 
     @staticmethod
     def from_configuration():
@@ -111,16 +112,38 @@ class Learner:
         T, B, A = c.UNROLL_STEP, c.BATCHSIZE, c.ACTION_SIZE
         dev = self.device
         state, action, mu, reward, done = [torch.as_tensor(x).to(dev) for x in transition]
+        fused = c.FUSED_CONV1 and state.dtype == torch.uint8 and self.model.first_conv_node() is not None
         with torch.no_grad():
-            s = state.float().div_(255.0).view(T + 1, B, 4, 84, 84)            # :131-140
-            last, seq = s[-1], s[:-1].reshape(-1, 4, 84, 84)
-            boot = (self.model.forward([last])[0][:, -1] * done.float().view(-1)).contiguous()   # :143
-            pi_a, value = self.forward(seq, action.reshape(-1))                 # :147
+            if fused:
+                # one launch: conv_1 of all (T+1)*B frame stacks, uint8 -> /255 folded in, no fp32 staging
+                if not hasattr(self, "_pack1"):
+                    self._conv_name = self.model.first_conv_node()
+                    self._pack1 = R.Conv1Pack(1, dev, getattr(self.model, self._conv_name).conv_1.out_channels)
+                w1 = getattr(self.model, self._conv_name).conv_1.weight
+                self._pack1.pack(0, w1)
+                frames = state.contiguous().view((T + 1) * B, 4, 84, 84)
+                y_all = R.conv1_fused(frames, None, self._pack1, relu=False)[0]
+                y_seq, y_last = y_all[:T * B], y_all[T * B:]
+                out_last = self.model.forward_from_conv1(y_last, False)[0]
+                out_seq = self.model.forward_from_conv1(y_seq, False)[0]
+            else:
+                s = state.float().div_(255.0).view(T + 1, B, 4, 84, 84)        # :131-140
+                last, seq = s[-1], s[:-1].reshape(-1, 4, 84, 84)
+                out_last = self.model.forward([last])[0]
+                out_seq = self.model.forward([seq])[0]
+            boot = (out_last[:, -1] * done.float().view(-1)).contiguous()       # :143
+            policy = torch.softmax(out_seq[:, :A], dim=-1)                      # forward(), :70-83
+            pi_a = policy.gather(1, action.reshape(-1, 1).long())[:, 0]
+            value = out_seq[:, -1]
             vt, adv = R.vtrace(pi_a.view(T, B).contiguous(), mu.float().view(T, B).contiguous(),
                                value.view(T, B).contiguous(), boot, reward.float().view(T, B).contiguous(),
                                c.GAMMA, c.C_LAMBDA, c.C_VALUE, c.P_VALUE)       # :151-215 in one launch
-        # calLoss (:95-119): second forward with grad
-        out = self.model.forward([seq])[0]
+        # calLoss (:95-119): second forward with grad (conv_1's output is reused: same weights, same frames)
+        if fused:
+            y = _Conv1Gathered.apply(w1, frames[:T * B], None, self._pack1, torch.contiguous_format, None, y_seq)
+            out = self.model.forward_from_conv1(y, False)[0]
+        else:
+            out = self.model.forward([seq])[0]
         logp = torch.log_softmax(out[:, :A], dim=-1)
         p = logp.exp()
         entropy = -(p * logp).sum(-1, keepdim=True)

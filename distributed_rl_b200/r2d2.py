@@ -166,9 +166,10 @@ class Learner:
         the uint8 -> /255 conversion are folded into the kernel's gather (row index = b*T + t)."""
         dev = self.device
         if not hasattr(self, "_pack2"):
-            self._pack2 = R.Conv1Pack(2, dev)
-            self._pack1 = R.Conv1Pack(1, dev)
             self._conv_name = self.model.first_conv_node()
+            c_out = getattr(self.model, self._conv_name).conv_1.out_channels
+            self._pack2 = R.Conv1Pack(2, dev, c_out)
+            self._pack1 = R.Conv1Pack(1, dev, c_out)
             t_idx = torch.arange(T, device=dev).view(T, 1)
             b_idx = torch.arange(B, device=dev).view(1, B)
             self._tm_rows = (b_idx * T + t_idx).reshape(-1).contiguous()      # time-major list of (b, t) rows

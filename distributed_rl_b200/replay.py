@@ -370,31 +370,32 @@ class Conv1Pack:
     """Packed conv_1 weights of 1 or 2 networks for b2rl_conv1_fused (re-pack after every
     optimizer step of the online net / target sync: one tiny launch per network)."""
 
-    def __init__(self, n_nets: int, device):
-        assert n_nets in (1, 2)
-        self.n_nets = n_nets
+    def __init__(self, n_nets: int, device, c_out: int = 32):
+        assert n_nets in (1, 2) and c_out in (16, 32)
+        self.n_nets, self.c_out = n_nets, c_out
         self.device = torch.device(device)
-        self.bq = torch.empty(n_nets * 128 * 256, dtype=torch.int8, device=self.device)
-        self.scale = torch.empty(n_nets * 32, dtype=torch.float32, device=self.device)
+        self.bq = torch.empty(n_nets * 4 * c_out * 256, dtype=torch.int8, device=self.device)
+        self.scale = torch.empty(n_nets * c_out, dtype=torch.float32, device=self.device)
 
     def pack(self, net: int, weight: torch.Tensor) -> None:
-        """weight: conv_1.weight fp32 (32, 4, 8, 8) (any memory format)."""
+        """weight: conv_1.weight fp32 (c_out, 4, 8, 8) (any memory format)."""
         w = weight.detach().to(torch.float32).contiguous(memory_format=torch.contiguous_format)
-        assert w.shape == (32, 4, 8, 8)
-        check(_lib.load().b2rl_conv1_pack(w.data_ptr(), net, self.n_nets, self.bq.data_ptr(),
+        assert w.shape == (self.c_out, 4, 8, 8)
+        check(_lib.load().b2rl_conv1_pack(w.data_ptr(), net, self.n_nets, self.c_out, self.bq.data_ptr(),
                                           self.scale.data_ptr(), _stream_ptr(self.device)))
 
 
 def conv1_fused(frames: torch.Tensor, idx, pack: Conv1Pack, relu: bool = False, out=None):
     """frames: uint8 (rows, 4, 84, 84) contiguous (e.g. DeviceReplay.field_view("state"));
     idx: int64[n] rows to take (None: all rows in order).
-    -> list of n_nets tensors (n, 32, 20, 20) fp32 in channels_last memory format."""
+    -> list of n_nets tensors (n, c_out, 20, 20) fp32 in channels_last memory format."""
     assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames[0].numel() == FRAME_STACK_BYTES
     n = frames.shape[0] if idx is None else idx.numel()
     dev = frames.device
     if out is None:
-        out = torch.empty((pack.n_nets, n, 20, 20, 32), dtype=torch.float32, device=dev)
+        out = torch.empty((pack.n_nets, n, 20, 20, pack.c_out), dtype=torch.float32, device=dev)
     check(_lib.load().b2rl_conv1_fused(frames.data_ptr(), frames.shape[0], None if idx is None else idx.data_ptr(),
-                                       n, pack.bq.data_ptr(), pack.scale.data_ptr(), pack.n_nets, out.data_ptr(),
+                                       n, pack.bq.data_ptr(), pack.scale.data_ptr(), pack.n_nets, pack.c_out,
+                                       out.data_ptr(),
                                        int(bool(relu)), _stream_ptr(dev)))
     return [out[i].permute(0, 3, 1, 2) for i in range(pack.n_nets)]   # logical NCHW, physical NHWC

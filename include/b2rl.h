@@ -206,16 +206,17 @@ int b2rl_vtrace(const float* pi_a_dev, const float* mu_a_dev, const float* value
  * (8x8, stride 4, 4 -> 32 channels, no bias; baseline/baseNetwork.py:165-172) applied to
  * frames[idx[k]] / 255 (APE_X/Learner.py:61-67,78,85,87) on the tcgen05 tensor cores, for one or
  * two networks (online + target) in one pass; the sampled uint8 frames are never staged in HBM.
- *   b2rl_conv1_pack   w_dev fp32 [32][4][8][8] of network `net` -> packed int8 digits
- *                     (bq_out: n_nets*128*256 bytes) and per-channel scale (scale_out: n_nets*32 fp32)
+ * c_out = 32 (cfg/ape_x.json, cfg/r2d2.json) or 16 (cfg/impala.json:25-37).
+ *   b2rl_conv1_pack   w_dev fp32 [c_out][4][8][8] of network `net` -> packed int8 digits
+ *                     (bq_out: n_nets*4*c_out*256 bytes) and per-channel scale (scale_out: n_nets*c_out fp32)
  *   b2rl_conv1_fused  frames_dev: rows of 28 224 bytes (e.g. b2rl_replay_field_ptr of the state
  *                     field), idx_dev int64[n] or NULL (rows 0..n-1), out_dev fp32
- *                     [n_nets][n][20][20][32] (NHWC), relu != 0 applies ReLU. */
-int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, int8_t* bq_out_dev,
+ *                     [n_nets][n][20][20][c_out] (NHWC), relu != 0 applies ReLU. */
+int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, int32_t c_out, int8_t* bq_out_dev,
                     float* scale_out_dev, void* stream);
 int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
-                     const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, float* out_dev,
-                     int32_t relu, void* stream);
+                     const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, int32_t c_out,
+                     float* out_dev, int32_t relu, void* stream);
 
 /* Learner.step (APE_X/Learner.py:123-138; IMPALA/Learner.py:258-266 without the clipping) with
  * torch.optim.RMSprop's update (baseline/utils.py getOptim :124-130; centered for Ape-X,

@@ -53,6 +53,23 @@ def test_conv1_fused_matches_fp64_convolution(R, n_nets, n, relu):
     np.testing.assert_allclose(outs2[0].cpu().double().numpy(), _ref(frames[:n], ws[0]).numpy(), rtol=0, atol=2e-6 * 8)
 
 
+@pytest.mark.parametrize("n_nets,n", [(1, 70), (2, 33)])
+def test_conv1_fused_16_channels_impala(R, n_nets, n):
+    """cfg/impala.json's conv_1 is 4 -> 16 channels: same kernel, C_OUT = 16 instantiation."""
+    rng = np.random.default_rng(n)
+    frames = rng.integers(0, 256, size=(n, 4, 84, 84), dtype=np.uint8)
+    ws = [torch.empty(16, 4, 8, 8).uniform_(-0.0625, 0.0625, generator=torch.Generator().manual_seed(3 + i))
+          for i in range(n_nets)]
+    pack = R.Conv1Pack(n_nets, "cuda:0", c_out=16)
+    for i, w in enumerate(ws):
+        pack.pack(i, w.cuda())
+    outs = R.conv1_fused(torch.from_numpy(frames).cuda(), None, pack, relu=True)
+    for o, w in zip(outs, ws):
+        want = _ref(frames, w).clamp_min(0)
+        assert o.shape == (n, 16, 20, 20)
+        assert (o.cpu().double() - want).abs().max().item() <= 2e-6 * max(want.abs().max().item(), 1.0)
+
+
 def test_conv1_fused_reads_replay_field_in_place(R):
     """Gather fused: rows come straight from the DeviceReplay payload (no staging copy)."""
     from oracle import oracle as O
