@@ -60,8 +60,7 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
     // +16 B so a 16-byte bulk/vector access on the last row never leaves the allocation
     alloc((void**)&h->field[f], (size_t)d->capacity * (size_t)d->field_bytes[f] + 16);
   }
-  h->geom = make_tree_geom(h->levels);
-  alloc((void**)&h->node, sizeof(TreeNode) * (size_t)h->geom.base[h->geom.nb]);
+  alloc((void**)&h->node, sizeof(TreeNode) * 2 * (size_t)h->cap2);
   alloc((void**)&h->tag, sizeof(uint32_t) * (size_t)h->cap2);
   alloc((void**)&h->mark, sizeof(int32_t) * (size_t)h->cap2);
   alloc((void**)&h->scratch_val, sizeof(float) * (size_t)h->capacity);

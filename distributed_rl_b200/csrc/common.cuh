@@ -123,45 +123,6 @@ __device__ __forceinline__ void st_node(TreeNode* p, double s, float m) {
   *reinterpret_cast<float4*>(p) = v;
 }
 
-// Cache-blocked placement of the implicit heap.  Heap node n (1 = root, children 2n / 2n+1, leaf j
-// = cap2 + j) at depth d is stored inside a 256-byte block that holds a 4-level subtree (15 nodes
-// in local heap order 1..15; the top block may be shorter), so a root-to-leaf walk touches ~2 cache
-// lines per FOUR levels instead of one sector per level, and the lines of a block are fetched
-// together.  All kernels keep using heap indices and translate with phys().
-struct TreeGeom {
-  int levels;        // leaves live at depth `levels`
-  int h0;            // height (number of depths) of the top block, 1..4
-  int nb;            // number of block levels
-  int64_t base[9];   // first slot of block level b; base[nb] = total slots
-};
-__host__ __device__ __forceinline__ int64_t tree_phys(const TreeGeom& G, int64_t n) {
-#ifdef __CUDA_ARCH__
-  const int d = 63 - __clzll((long long)n);
-#else
-  int d = 0;
-  while ((n >> (d + 1)) != 0) ++d;
-#endif
-  const int64_t i = n - ((int64_t)1 << d);
-  if (d < G.h0) return ((int64_t)1 << d) + i;                       // top block: local heap order
-  const int b = 1 + ((d - G.h0) >> 2), r = (d - G.h0) & 3;
-  return G.base[b] + ((i >> r) << 4) + ((int64_t)1 << r) + (i & (((int64_t)1 << r) - 1));
-}
-inline TreeGeom make_tree_geom(int levels) {
-  TreeGeom G{};
-  G.levels = levels;
-  const int D = levels + 1;
-  G.nb = (D + 3) / 4;
-  G.h0 = D - 4 * (G.nb - 1);
-  G.base[0] = 0;
-  int64_t slots = 16;                                               // the single top block
-  for (int b = 1; b <= G.nb; ++b) {
-    G.base[b] = G.base[b - 1] + slots;
-    const int rd = G.h0 + 4 * (b - 1);                              // depth of block level b's roots
-    slots = ((int64_t)1 << rd) * 16;
-  }
-  return G;
-}
-
 // The opaque handle.
 struct b2rl_replay {
   int device = 0;
@@ -171,8 +132,7 @@ struct b2rl_replay {
   int n_fields = 0;
   int64_t field_bytes[B2RL_MAX_FIELDS] = {0};
   uint8_t* field[B2RL_MAX_FIELDS] = {nullptr};
-  TreeNode* node = nullptr;   // [geom.base[geom.nb]] cache-blocked implicit heap (see TreeGeom)
-  TreeGeom geom{};
+  TreeNode* node = nullptr;   // [2*cap2] implicit heap, node 1 = root, leaf j = cap2 + j
   uint32_t* tag = nullptr;    // [cap2]   last-writer tags, self-cleaning
   int32_t* mark = nullptr;    // [cap2]   per-internal-node side bits + arrival count, self-cleaning
   int64_t* scratch_idx = nullptr;  // [capacity] ring indices for push/evict

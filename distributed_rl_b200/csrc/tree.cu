@@ -30,8 +30,7 @@ constexpr int BUILD_PER_THREAD = BUILD_CHUNK / 2 / BUILD_THREADS;  // 4
 // fp64 leaves, reduces the bottom levels of its subtree in shared memory and
 // writes every node out; its subtree root lands at heap index cap2/2048 + c.
 __global__ void __launch_bounds__(BUILD_THREADS)
-k_build_bottom(const float* __restrict__ prios, int64_t n_valid, TreeNode* __restrict__ node, int64_t cap2,
-               const TreeGeom G) {
+k_build_bottom(const float* __restrict__ prios, int64_t n_valid, TreeNode* __restrict__ node, int64_t cap2) {
   __shared__ double s_sum[BUILD_CHUNK];
   __shared__ float s_min[BUILD_CHUNK];
   const int64_t leaf0 = (int64_t)blockIdx.x * BUILD_CHUNK;
@@ -42,7 +41,7 @@ k_build_bottom(const float* __restrict__ prios, int64_t n_valid, TreeNode* __res
     const float m = (p > 0.0f) ? p : INFINITY;
     s_sum[i] = (double)p;
     s_min[i] = m;
-    st_node(node + tree_phys(G, cap2 + j), (double)p, m);
+    st_node(node + cap2 + j, (double)p, m);
   }
   __syncthreads();
   int per = 2;  // leaves per node of the level being produced
@@ -60,7 +59,7 @@ k_build_bottom(const float* __restrict__ prios, int64_t n_valid, TreeNode* __res
     for (int i = threadIdx.x; i < w; i += BUILD_THREADS, ++c) {
       s_sum[i] = ts[c];
       s_min[i] = tm[c];
-      st_node(node + tree_phys(G, base + i), ts[c], tm[c]);
+      st_node(node + base + i, ts[c], tm[c]);
     }
     __syncthreads();
   }
@@ -69,15 +68,16 @@ k_build_bottom(const float* __restrict__ prios, int64_t n_valid, TreeNode* __res
 // Levels above the 2048-leaf subtrees: `m` = cap2/2048 nodes on the deepest of
 // them.  One CTA, level-synchronous (at most 12 levels for cap2 = 2^23).
 __global__ void __launch_bounds__(1024)
-k_build_top(TreeNode* __restrict__ node, int64_t m, const TreeGeom G) {
+k_build_top(TreeNode* __restrict__ node, int64_t m) {
   for (int64_t w = m / 2; w >= 1; w >>= 1) {
     for (int64_t i = threadIdx.x; i < w; i += blockDim.x) {
       const int64_t nd = w + i;
-      const TreeNode a = ld_node(node + tree_phys(G, 2 * nd)), b = ld_node(node + tree_phys(G, 2 * nd + 1));
-      st_node(node + tree_phys(G, nd), a.s + b.s, fminf(a.m, b.m));
+      const TreeNode a = ld_node(node + 2 * nd), b = ld_node(node + 2 * nd + 1);
+      st_node(node + nd, a.s + b.s, fminf(a.m, b.m));
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) st_node(node, 0.0, INFINITY);
 }
 
 // ----------------------------------------------------------------------------
@@ -86,7 +86,7 @@ k_build_top(TreeNode* __restrict__ node, int64_t m, const TreeGeom G) {
 constexpr int SAMPLE_THREADS = 128;
 
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-k_tree_sample(const TreeNode* __restrict__ node, const TreeGeom G, int64_t cap2,
+k_tree_sample(const TreeNode* __restrict__ node, int64_t cap2,
               int levels, const double* __restrict__ u01, uint64_t seed, uint64_t rng_offset,
               const uint64_t* __restrict__ rng_state, int64_t n, float n_valid, float beta,
               const float* __restrict__ max_w_ext, int64_t* __restrict__ idx_out,
@@ -108,19 +108,13 @@ k_tree_sample(const TreeNode* __restrict__ node, const TreeGeom G, int64_t cap2,
     }
   }
   if (k >= n) return;
-  const TreeNode rootn = ld_node(node + tree_phys(G, 1));
+  const TreeNode rootn = ld_node(node + 1);
   const double root = rootn.s;
   const double u = u01 ? u01[k] : philox_u01(seed, rng_offset + (uint64_t)k);
   double pos = __dmul_rn(root, u);  // np.random.uniform(0, root) == root * random_sample()
   int64_t i = 1;
   for (int l = 0; l < levels; ++l) {
-    const int64_t pl = tree_phys(G, 2 * i), pr = tree_phys(G, 2 * i + 1);
-    const double cl = node[pl].s, cr = node[pr].s;   // adjacent slots inside a block; two block roots at a boundary
-    // entering a new 4-level block: pull its second cache line (local depths 3) now, in parallel
-    if (((l + 1 - G.h0) & 3) == 0 && l + 1 >= G.h0) {
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(node + pl + 7));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(node + pr + 7));
-    }
+    const double cl = node[2 * i].s, cr = node[2 * i + 1].s;   // both children live in one 32-byte sector
     // Node._find: left iff pos < left.  The `cr == 0` guard only matters when
     // pos rounds up to the subtree total (the reference dereferences None there).
     const bool left = (pos < cl) || (cr == 0.0);
@@ -132,7 +126,7 @@ k_tree_sample(const TreeNode* __restrict__ node, const TreeGeom G, int64_t cap2,
   if (prob_out == nullptr && w_out == nullptr) return;
   // APE_X/ReplayMemory.py:65-67, baseline/PER.py:98,129-133 — fp32 op by op.
   const float s32 = (float)root;
-  const float p = (float)node[tree_phys(G, i)].s;
+  const float p = (float)node[i].s;
   const float prob = __fdiv_rn(p, s32);
   if (prob_out) prob_out[k] = prob;
   if (w_out) {
@@ -157,9 +151,9 @@ __global__ void k_philox_uniforms(uint64_t seed, uint64_t off, int64_t n, double
   if (k < n) out[k] = philox_u01(seed, off + (uint64_t)k);
 }
 
-__global__ void k_tree_stats(const TreeNode* __restrict__ node, const TreeGeom G, float n_valid, float beta,
+__global__ void k_tree_stats(const TreeNode* __restrict__ node, float n_valid, float beta,
                              double* __restrict__ out, float* __restrict__ max_w_out) {
-  const TreeNode r = ld_node(node + tree_phys(G, 1));
+  const TreeNode r = ld_node(node + 1);
   const double root = r.s;
   const float s32 = (float)root;
   const float mn = r.m;
@@ -168,10 +162,10 @@ __global__ void k_tree_stats(const TreeNode* __restrict__ node, const TreeGeom G
   if (max_w_out) *max_w_out = mw;
 }
 
-__global__ void k_tree_leaves(const TreeNode* __restrict__ node, const TreeGeom G, int64_t cap2, int64_t start,
-                              int64_t n, float* __restrict__ out) {
+__global__ void k_tree_leaves(const TreeNode* __restrict__ node, int64_t cap2, int64_t start, int64_t n,
+                              float* __restrict__ out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) out[k] = (float)node[tree_phys(G, cap2 + start + k)].s;
+  if (k < n) out[k] = (float)node[cap2 + start + k].s;
 }
 
 // ----------------------------------------------------------------------------
@@ -208,7 +202,7 @@ k_update_tag(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capaci
 __global__ void __launch_bounds__(UPD_THREADS)
 k_update_write(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
                const float* __restrict__ vals, float const_val, int64_t n,
-               const uint32_t* __restrict__ tag, TreeNode* __restrict__ tree, const TreeGeom G,
+               const uint32_t* __restrict__ tag, TreeNode* __restrict__ tree,
                int32_t* __restrict__ mark, int64_t cap2, int levels) {
   const int64_t k = (int64_t)blockIdx.x * UPD_THREADS + threadIdx.x;
   if (k >= n) return;
@@ -217,7 +211,7 @@ k_update_write(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
   if (tag[j] != (uint32_t)(k + 1)) return;  // a later k wrote the same slot
   const float p = vals ? vals[k] : const_val;
   int64_t node = cap2 + j;
-  st_node(tree + tree_phys(G, node), (double)p, (p > 0.0f) ? p : INFINITY);
+  st_node(tree + node, (double)p, (p > 0.0f) ? p : INFINITY);
   for (int l = 0; l < levels; ++l) {
     const int bit = (node & 1) ? 2 : 1;
     node >>= 1;
@@ -228,7 +222,7 @@ k_update_write(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
 
 __global__ void __launch_bounds__(UPD_THREADS)
 k_update_climb(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity, int64_t n,
-               uint32_t* __restrict__ tag, TreeNode* __restrict__ tree, const TreeGeom G,
+               uint32_t* __restrict__ tag, TreeNode* __restrict__ tree,
                int32_t* __restrict__ mark, int64_t cap2, int levels) {
   const int64_t k = (int64_t)blockIdx.x * UPD_THREADS + threadIdx.x;
   if (k >= n) return;
@@ -243,8 +237,8 @@ k_update_climb(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capa
     const int old = atomicAdd(mark + node, 4);     // arrivals live above the two side bits
     if ((old >> 2) + 1 < __popc(old & 3)) return;  // the other touched child arrives later
     __threadfence();                               // acquire: see the other subtree's writes
-    const TreeNode a = ld_node_cg(tree + tree_phys(G, 2 * node)), b = ld_node_cg(tree + tree_phys(G, 2 * node + 1));
-    st_node(tree + tree_phys(G, node), a.s + b.s, fminf(a.m, b.m));
+    const TreeNode a = ld_node_cg(tree + 2 * node), b = ld_node_cg(tree + 2 * node + 1);
+    st_node(tree + node, a.s + b.s, fminf(a.m, b.m));
     mark[node] = 0;                                // self-clean: nobody else visits this node now
   }
 }
@@ -268,7 +262,7 @@ constexpr int US_MAX_LEVELS = 24;
 __global__ void __launch_bounds__(US_THREADS, 1)
 k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
                 const float* __restrict__ vals, float const_val, int n, TreeNode* __restrict__ tree,
-                const TreeGeom G, int64_t cap2, int levels) {
+                int64_t cap2, int levels) {
   __shared__ uint64_t s_key[US_THREADS];
   __shared__ uint32_t s_leaf[US_THREADS];
   __shared__ float s_valf[US_THREADS];
@@ -318,7 +312,7 @@ k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t cap
   for (int l = 0; l < US_MAX_LEVELS; ++l) {
     if (valid && l < levels) {
       const int64_t node = ((cap2 + (int64_t)leaf) >> l) ^ 1;   // heap index of the sibling
-      const TreeNode sib = ld_node_cg(tree + tree_phys(G, node));   // one 16-byte request per level
+      const TreeNode sib = ld_node_cg(tree + node);             // one 16-byte request per level
       pre_sum[l] = sib.s;
       pre_min[l] = sib.m;
     } else { pre_sum[l] = 0.0; pre_min[l] = INFINITY; }
@@ -339,7 +333,7 @@ k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t cap
   const float vwin = valid ? s_valf[hi - 1] : 0.0f;          // last writer wins
   double cur_sum = (double)vwin;
   float cur_min = (vwin > 0.0f) ? vwin : INFINITY;
-  if (valid && t == lo) st_node(tree + tree_phys(G, cap2 + leaf), cur_sum, cur_min);
+  if (valid && t == lo) st_node(tree + cap2 + leaf, cur_sum, cur_min);
 #pragma unroll
   for (int l = 0; l < US_MAX_LEVELS; ++l) {
     if (l >= levels) break;
@@ -363,7 +357,7 @@ k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t cap
     }
     __syncthreads();
     if (valid && t == lo) {
-      st_node(tree + tree_phys(G, (cap2 + (int64_t)leaf) >> (l + 1)), cur_sum, cur_min);
+      st_node(tree + ((cap2 + (int64_t)leaf) >> (l + 1)), cur_sum, cur_min);
     }
   }
 }
@@ -391,7 +385,7 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
       k_update_sorted<<<1, US_THREADS, 0, st>>>(idx_dev ? idx_dev + off : nullptr,
                                                 (ring_start + off) % h->capacity, h->capacity,
                                                 vals_dev ? vals_dev + off : nullptr, const_val, m, h->node,
-                                                h->geom, h->cap2, h->levels);
+                                                h->cap2, h->levels);
       count_launch();
     }
     B2RL_CHECK_LAUNCH();
@@ -400,9 +394,9 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
   const unsigned g = grid_for(n, UPD_THREADS);
   k_update_tag<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag);
   k_update_write<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, vals_dev, const_val, n,
-                                            h->tag, h->node, h->geom, h->mark, h->cap2, h->levels);
+                                            h->tag, h->node, h->mark, h->cap2, h->levels);
   k_update_climb<<<g, UPD_THREADS, 0, st>>>(idx_dev, ring_start, h->capacity, n, h->tag, h->node,
-                                            h->geom, h->mark, h->cap2, h->levels);
+                                            h->mark, h->cap2, h->levels);
   count_launch(3);
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
@@ -415,10 +409,10 @@ extern "C" int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t chunks = (h->cap2 + BUILD_CHUNK - 1) / BUILD_CHUNK;
-  k_build_bottom<<<(unsigned)chunks, BUILD_THREADS, 0, st>>>(prios_dev, n, h->node, h->cap2, h->geom);
+  k_build_bottom<<<(unsigned)chunks, BUILD_THREADS, 0, st>>>(prios_dev, n, h->node, h->cap2);
   count_launch();
   if (h->cap2 > BUILD_CHUNK) {
-    k_build_top<<<1, 1024, 0, st>>>(h->node, h->cap2 / BUILD_CHUNK, h->geom);
+    k_build_top<<<1, 1024, 0, st>>>(h->node, h->cap2 / BUILD_CHUNK);
     count_launch();
   }
   B2RL_CHECK_LAUNCH();
@@ -438,7 +432,7 @@ extern "C" int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t 
   if (n == 0) return B2RL_OK;
   DeviceGuard g(h->device);
   k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(
-      h->node, h->geom, h->cap2, h->levels, u01_dev, seed, rng_offset, nullptr, n, (float)h->size, beta,
+      h->node, h->cap2, h->levels, u01_dev, seed, rng_offset, nullptr, n, (float)h->size, beta,
       max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
@@ -465,7 +459,7 @@ extern "C" int b2rl_tree_sample_stream(b2rl_replay* h, int64_t n, float beta, co
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, st>>>(
-      h->node, h->geom, h->cap2, h->levels, nullptr, 0, 0, h->rng_dev, n, (float)h->size, beta,
+      h->node, h->cap2, h->levels, nullptr, 0, 0, h->rng_dev, n, (float)h->size, beta,
       max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
@@ -496,7 +490,7 @@ extern "C" int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev
                                void* stream) {
   B2RL_REQUIRE(h != nullptr && (stats_out_dev != nullptr || max_w_out_dev != nullptr), "null argument");
   DeviceGuard g(h->device);
-  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->node, h->geom, (float)h->size, beta, stats_out_dev,
+  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->node, (float)h->size, beta, stats_out_dev,
                                                   max_w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
@@ -509,7 +503,7 @@ extern "C" int b2rl_tree_leaves(b2rl_replay* h, int64_t start, int64_t n, float*
   if (n == 0) return B2RL_OK;
   B2RL_REQUIRE(out_dev != nullptr, "null out");
   DeviceGuard g(h->device);
-  k_tree_leaves<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->node, h->geom, h->cap2, start, n, out_dev);
+  k_tree_leaves<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->node, h->cap2, start, n, out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
