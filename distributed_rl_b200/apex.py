@@ -272,6 +272,10 @@ class Learner:
         self._D = D
         self._world = D.world()
         self._bucket = D.FlatGradBucket(self.model.getParameters(), self.device)
+        # the dense heads hold 97 % of the parameters and their gradients are complete first in the
+        # backward pass: their all-reduce overlaps the backward of the convolution stack
+        heads = [p for p in self.model.getParameters() if p.dim() == 2]
+        self._bucket.enable_overlap(heads)
         self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)
 
     def build_model(self):
@@ -314,7 +318,7 @@ class Learner:
                             self.gamma_n, self.cfg.ALPHA)
         q.backward(out["grad_q"])                      # == loss.backward(), :112-115
         if self._world > 1:
-            self._bucket.all_reduce_mean()
+            self._bucket.finish()
         return out
 
     def train(self, transition, t=0):
@@ -373,7 +377,7 @@ class Learner:
                             self.gamma_n, self.cfg.ALPHA)
         q.backward(out["grad_q"])
         if self._world > 1:
-            self._bucket.all_reduce_mean()
+            self._bucket.finish()
         return out
 
     # -- the whole hot loop iteration as one CUDA graph -----------------------------------

@@ -31,14 +31,60 @@ class FlatGradBucket:
             p.grad = self.flat[off:off + p.numel()].as_strided(p.shape, p.stride())
             off += p.numel()
 
+    def _reduce(self, t: torch.Tensor, async_op: bool = False):
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)     # gloo has no AVG
+        if not async_op:
+            t.div_(world())
+        return w
+
     def all_reduce_mean(self) -> None:
         if world() == 1:
             return
-        if dist.get_backend() == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
-        else:                                   # gloo has no AVG
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(world())
+        self._reduce(self.flat)
+
+    # -- overlap: reduce the gradients that are ready EARLY in the backward pass (the big head
+    #    matrices, 97 % of the bytes) while the backward of the convolution stack still runs ----
+    def enable_overlap(self, early_params) -> None:
+        """`early_params`: parameters whose gradients are complete first (must be a prefix or any
+        subset; they are moved to the front of the bucket).  Their all-reduce is launched from a
+        post-accumulate hook on the LAST of them; call finish() after backward."""
+        early = [p for p in self.params if any(p is q for q in early_params)]
+        late = [p for p in self.params if not any(p is q for q in early_params)]
+        self.params = early + late
+        off = 0
+        for p in self.params:                       # re-lay the bucket: early params first
+            p.grad = self.flat[off:off + p.numel()].as_strided(p.shape, p.stride())
+            off += p.numel()
+        n_early = sum(p.numel() for p in early)
+        self._early, self._late = self.flat[:n_early], self.flat[n_early:]
+        self._pending, self._seen, self._work = len(early), 0, None
+        gloo = dist.is_initialized() and dist.get_backend() != "nccl"
+
+        def hook(_p):
+            self._seen += 1
+            if self._seen == self._pending and world() > 1:
+                self._work = self._reduce(self._early, async_op=True)
+                self._early_needs_div = gloo
+
+        for p in early:
+            p.register_post_accumulate_grad_hook(hook)
+
+    def finish(self) -> None:
+        """After backward: reduce the late (small) part, then wait for the early part."""
+        if world() == 1:
+            self._seen = 0
+            return
+        if self._late.numel():
+            self._reduce(self._late)
+        if self._work is not None:
+            self._work.wait()
+            if getattr(self, "_early_needs_div", False):
+                self._early.div_(world())
+        else:                                       # hooks did not fire (no early grads): reduce now
+            self._reduce(self._early)
+        self._work, self._seen = None, 0
 
 
 def all_reduce_max_(x: torch.Tensor) -> torch.Tensor:

@@ -35,6 +35,19 @@ def _worker(rank, world, port, q):
     dist.all_gather(both, local)
     out["bucket_ok"] = bool(torch.allclose(bucket.flat, sum(both) / world))
     out["views_ok"] = all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())
+    # 1b. overlapped variant: early params reduced from the autograd hook, late ones in finish()
+    lin2 = torch.nn.Sequential(torch.nn.Linear(4, 3, bias=False), torch.nn.Linear(3, 2, bias=False))
+    b2 = D.FlatGradBucket(lin2.parameters())
+    b2.enable_overlap([lin2[1].weight])          # the last layer's gradient is ready first
+    lin2(x).sum().backward()
+    local2 = [p.grad.clone() for p in lin2.parameters()]
+    b2.finish()
+    ok = True
+    for p, l in zip(lin2.parameters(), local2):
+        g = [torch.zeros_like(l) for _ in range(world)]
+        dist.all_gather(g, l)
+        ok = ok and bool(torch.allclose(p.grad, sum(g) / world))
+    out["overlap_ok"] = ok
     # 2. priority-max reduction: shard-local IS weights / global max == single-replay formula
     n, beta = 1024, 0.4
     rng = np.random.default_rng(100 + rank)
@@ -77,6 +90,7 @@ def test_world2_gloo_data_parallel_logic():
         assert p.exitcode == 0
     for r in (0, 1):
         assert res[r]["bucket_ok"] and res[r]["views_ok"] and res[r]["isw_ok"] and res[r]["shard_ok"], res[r]
+        assert res[r]["overlap_ok"], res[r]
     assert res[0]["mw"] == res[1]["mw"]
 
 
