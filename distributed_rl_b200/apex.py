@@ -274,8 +274,9 @@ class Learner:
         self._bucket = D.FlatGradBucket(self.model.getParameters(), self.device)
         # the dense heads hold 97 % of the parameters and their gradients are complete first in the
         # backward pass: their all-reduce overlaps the backward of the convolution stack
+        import os
         heads = [p for p in self.model.getParameters() if p.dim() == 2]
-        self._bucket.enable_overlap(heads)
+        self._bucket.enable_overlap([] if os.environ.get("B2RL_NO_OVERLAP") else heads)
         self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)
 
     def build_model(self):
