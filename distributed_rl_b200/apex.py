@@ -277,7 +277,8 @@ class Learner:
         import os
         heads = [p for p in self.model.getParameters() if p.dim() == 2]
         self._bucket.enable_overlap([] if os.environ.get("B2RL_NO_OVERLAP") else heads)
-        self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)
+        self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)       # being reduced this step
+        self._max_w_use = None                                                      # reduced last step, used now
 
     def build_model(self):
         self.model = GraphAgent(self.cfg.MODEL).to(self.device)
@@ -393,9 +394,13 @@ class Learner:
         fused_conv1 = self._conv1_ready()
 
         def body():
-            max_w = None
-            if self._world > 1:      # priority-max reduction: normalise IS weights by the global max
-                max_w = self._D.all_reduce_max_(st.max_weight(self.cfg.BETA, out=self._max_w))
+            max_w, mw_work = None, None
+            if self._world > 1:
+                # priority-max reduction: IS weights are normalised by the GLOBAL max weight.  The MAX
+                # all-reduce of this step's local value runs behind the step and is used by the next one
+                # (the reference's own max_weight is up to 16 minibatches stale, APE_X/ReplayMemory.py:61-67).
+                mw_work = self._D.all_reduce_max_(st.max_weight(self.cfg.BETA, out=self._max_w), async_op=True)
+                max_w = self._max_w_use
             idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
             if fused_conv1:
                 if not hasattr(self, "_small"):
@@ -408,9 +413,14 @@ class Learner:
                                              b["next_state"], b["done"], w)
             info = self.step()
             st.update(idx, out["prio"])
+            if mw_work is not None:
+                mw_work.wait()
+                self._max_w_use.copy_(self._max_w)
             return {"scalars": out["scalars"], "p_norm": info["p_norm"], "prio": out["prio"], "idx": idx}
 
         lib = st.lib
+        if self._world > 1 and self._max_w_use is None:      # first step: reduce synchronously once
+            self._max_w_use = self._D.all_reduce_max_(st.max_weight(self.cfg.BETA)).clone()
         if not use_graph:
             c0 = lib.b2rl_launch_count()
             r = body()

@@ -87,11 +87,13 @@ class FlatGradBucket:
         self._work, self._seen = None, 0
 
 
-def all_reduce_max_(x: torch.Tensor) -> torch.Tensor:
-    """In-place MAX all-reduce of the shard-local max IS weight."""
+def all_reduce_max_(x: torch.Tensor, async_op: bool = False):
+    """In-place MAX all-reduce of the shard-local max IS weight.  async_op=True returns the work
+    handle (None at world size 1) so the tiny collective can hide behind the learner step."""
     if world() > 1:
-        dist.all_reduce(x, op=dist.ReduceOp.MAX)
-    return x
+        w = dist.all_reduce(x, op=dist.ReduceOp.MAX, async_op=async_op)
+        return w if async_op else x
+    return None if async_op else x
 
 
 def shard_slots(total_slots: int, rank: int, world_size: int) -> range:
