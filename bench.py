@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.RMSprop instead of the fused kernel")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="leave cuDNN's algorithm choice to its heuristics")
     ap.add_argument("--blaslt", action="store_true", help="route fp32 GEMMs through cuBLASLt")
+    ap.add_argument("--tf32-matmul", action="store_true",
+                    help="INFORMATIONAL ONLY: let the dense heads use TF32 like cuDNN's convolutions already do "
+                         "(PyTorch's default, which the reference runs, is fp32 matmul; the headline keeps fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=48)
     return ap.parse_args()
@@ -178,7 +181,8 @@ def workload_config(args, world):
             "record_bytes": ALG_BYTES_PER_TRANSITION_GATHER,
             "parallelism": f"replay-sharded dp{world}" if world > 1 else "single GPU",
             "l2": "inputs >> L2: every step gathers random rows of a 59 GB payload (no L2 flush needed)",
-            "network": "dueling DQN of cfg/ape_x.json in PyTorch (fp32, cuDNN TF32 convs = torch defaults)"}
+            "network": "dueling DQN of cfg/ape_x.json; conv_1 fused with the gather on tcgen05 (int8 digits, fp32-exact), "
+                       "rest in PyTorch at its default precision (fp32 matmul, TF32 cuDNN convs) = what the reference runs"}
 
 
 # --------------------------------------------------------------------------- #
@@ -207,6 +211,8 @@ def main():
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     if args.blaslt:
         torch.backends.cuda.preferred_blas_library("cublaslt")
+    if args.tf32_matmul:
+        torch.backends.cuda.matmul.allow_tf32 = True
     if world > 1:
         os.environ.pop("NCCL_DEBUG", None)      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -404,7 +410,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "clocks": clock_info,
-                "cuda_graph": use_graph, "fused_gather_conv1": bool(cfg.FUSED_CONV1), "fused_optimizer": bool(cfg.FUSED_OPTIM), "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
+                "cuda_graph": use_graph, "fused_gather_conv1": bool(cfg.FUSED_CONV1), "fused_optimizer": bool(cfg.FUSED_OPTIM), "tf32_matmul": bool(args.tf32_matmul), "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:
