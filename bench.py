@@ -390,6 +390,7 @@ def main():
         ms2 = float(t.item())
     e2e = {"value": B * world * k2 / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 12, "steps": k2,
+           "h2d_GBs": h2d * k2 / (ms2 / 1e3) / 1e9,
            "what": "Replay.commit_ingest + begin_ingest (512 new transitions from pinned host, H2D on the ingest "
                    "stream overlapping the step) + Learner.fused_step() + per-step D2H of the step's scalars to pinned "
                    "host memory (consumed by the host one step later)"}
