@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="keep the network in NCHW (default: channels_last)")
     ap.add_argument("--unfused-conv1", action="store_true", help="stage the batch and let cuDNN run conv_1")
+    ap.add_argument("--cublas-dense", action="store_true", help="dense heads as cuBLAS fp32 GEMMs instead of the 3xTF32 tcgen05 kernel (csrc/gemm.cu)")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.RMSprop instead of the fused kernel")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="leave cuDNN's algorithm choice to its heuristics")
     ap.add_argument("--blaslt", action="store_true", help="route fp32 GEMMs through cuBLASLt")
@@ -221,7 +222,7 @@ def main():
     N, B = 1 << args.log2n, args.batch
     cfg = ApexConfig(BATCHSIZE=B, REPLAY_MEMORY_LEN=N, BUFFER_SIZE=0, LEARNER_DEVICE=str(dev),
                      CHANNELS_LAST=not args.nchw, FUSED_CONV1=not args.unfused_conv1,
-                     FUSED_OPTIM=not args.torch_optim)
+                     FUSED_OPTIM=not args.torch_optim, DENSE_3XTF32=not args.cublas_dense)
     torch.manual_seed(0)
     learner = Learner(cfg, connect=None, start_replay=False)
     if world > 1:   # identical initial weights on every rank
@@ -411,7 +412,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "clocks": clock_info,
-                "cuda_graph": use_graph, "fused_gather_conv1": bool(cfg.FUSED_CONV1), "fused_optimizer": bool(cfg.FUSED_OPTIM), "tf32_matmul": bool(args.tf32_matmul), "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
+                "cuda_graph": use_graph, "fused_gather_conv1": bool(cfg.FUSED_CONV1), "fused_optimizer": bool(cfg.FUSED_OPTIM), "tf32_matmul": bool(args.tf32_matmul), "dense_3xtf32": bool(cfg.DENSE_3XTF32), "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:

@@ -189,6 +189,7 @@ class GraphAgent(nn.Module):
         # Sibling MLP heads fed by the same node (the dueling adv/val heads): their first Linear layers
         # share the input, so they run as ONE GEMM on the concatenated weights (same maths, wider N).
         self.fuse_sibling_heads = True
+        self.dense_3xtf32 = False       # first Linear of fused sibling heads via linear.linear3x (csrc/gemm.cu)
         groups = {}
         for name in order:
             m = getattr(self, name)
@@ -211,7 +212,11 @@ class GraphAgent(nn.Module):
                 if name not in first_out:
                     x = vals[self._prev[name][0]]
                     ws = [next(iter(getattr(self, n).children())).weight for n in group]
-                    h = torch.nn.functional.linear(x, torch.cat(ws, 0))
+                    if self.dense_3xtf32 and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32:
+                        from .linear import linear3x
+                        h = linear3x(x, torch.cat(ws, 0))
+                    else:
+                        h = torch.nn.functional.linear(x, torch.cat(ws, 0))
                     for n, part in zip(group, torch.split(h, [w.shape[0] for w in ws], dim=-1)):
                         first_out[n] = part
                 vals[name] = getattr(self, name).forward_after_first(first_out[name])

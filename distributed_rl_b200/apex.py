@@ -53,6 +53,7 @@ class ApexConfig:
     FUSED_CONV1: bool = True        # gather + conv_1 on the tcgen05 tensor cores (csrc/conv1.cu) in fused_step
     FUSED_OPTIM: bool = True        # RMSprop + zero_grad + grad-norm in one launch (csrc/optim.cu)
     CUDNN_BENCHMARK: bool = True    # let cuDNN time its conv_2/conv_3 algorithms once (no precision change)
+    DENSE_3XTF32: bool = True       # dense heads as 3xTF32 tcgen05 GEMMs at fp32 accuracy (csrc/gemm.cu)
 
     @staticmethod
     def from_configuration():
@@ -287,6 +288,7 @@ class Learner:
         if self.cfg.CHANNELS_LAST:
             self.model.to(memory_format=torch.channels_last)
             self.target_model.to(memory_format=torch.channels_last)
+        self.model.dense_3xtf32 = self.target_model.dense_3xtf32 = bool(self.cfg.DENSE_3XTF32)
 
     def build_optim(self):
         info = self.cfg.OPTIM_INFO

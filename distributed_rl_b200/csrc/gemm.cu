@@ -1,0 +1,325 @@
+// fp32-accurate dense layers on the tensor cores: C[M][N] (+)= A[M][K] * B[N][K]^T with 3xTF32.
+//
+// The dense heads of the Q-network (3136 -> 512, twice; cfg/ape_x.json:52-71) run as cuBLAS fp32
+// SIMT GEMMs at PyTorch's default precision and are 31 % of the learner step.
+// TF32 alone (10-bit mantissa) is not what the reference computes, so every fp32 operand is split
+//      x = hi + lo,   hi = rn_tf32(x),  lo = x - hi   (exact in fp32)
+// and the product is formed as  hi*hi + hi*lo + lo*hi  on tcgen05 (kind::tf32, fp32 accumulation in
+// TMEM); the dropped lo*lo term is 2^-22 relative.  SURVEY.md §8f rank 2 ("TF32x3 policy").
+//
+//   k_split_pack   fp32 matrix (optionally transposed) -> {hi, lo} operand images in exactly the
+//                  128B-swizzled, K-major tile layout the MMA reads, so the GEMM's loader is a
+//                  plain cp.async.bulk per tile (no tensor map, no SM-side staging)
+//   k_gemm_tf32x3  one CTA per (m-tile 128, n-tile 256, K-split): TMA loader warp, one MMA-issuing
+//                  thread (12 x tcgen05.mma per 32-float K chunk), 4 epilogue warps that add the
+//                  partial tile into C with coalesced vector reductions
+#include "common.cuh"
+
+namespace b2rl {
+namespace gemm {
+
+constexpr int TM = 128, TN = 256, KC = 32;          // tile rows of A / of B, floats per K chunk (128 B)
+constexpr int A_TILE = TM * 128, B_TILE = TN * 128;  // bytes of one {term, k-chunk} tile: 16 KiB / 32 KiB
+constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;       // hi+lo of both operands: 96 KiB
+constexpr int STAGES = 2;
+constexpr int THREADS = 224;                         // warp 0 loader, 1 MMA, 2 TMEM alloc, 3-6 epilogue
+
+__device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(c));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(sptr(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   sptr(dst)), "l"(src), "r"(bytes), "r"(sptr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc),
+      "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// K-major SW128 descriptor (see csrc/conv1.cu): SBO = 1024 B, LBO = 16 B, version 1, layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, N>>3 @17, M>>4 @24
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// ---- operand packing ---------------------------------------------------------
+// Image layout: [term 0=hi,1=lo][k_chunk][row_tile][row_in_tile][128 B, 16-byte units XOR (row & 7)]
+// One CTA per (32 operand rows, one K chunk); thread = (row r = tid / 8, 16-byte unit = tid % 8), so
+// both the source row segment and the image row are one contiguous 128 B per 8 threads.
+// TRANSPOSE: the operand's rows are the source's columns; the 32x32 block goes through SMEM so that
+// the source is still read along its contiguous dimension.
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  const uint32_t u = __float_as_uint(x);
+  uint32_t h = (u + 0x1000u) & 0xFFFFE000u;                        // round to nearest on the 13 dropped bits
+  if ((h & 0x7F800000u) == 0x7F800000u) h = u & 0xFFFFE000u;        // rounding reached inf (or x is inf/nan): truncate
+  hi = __uint_as_float(h);
+  lo = ((u & 0x7F800000u) == 0x7F800000u) ? 0.0f : x - hi;          // exact in fp32
+  if ((u & 0x7F800000u) == 0x7F800000u) hi = x;
+}
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(256)
+k_split_pack(const float* __restrict__ src, int src_rows, int src_cols, int64_t src_ld, int tile_rows,
+             float* __restrict__ out, int rows_pad, int k_chunks) {
+  const int kc = blockIdx.y, row0 = blockIdx.x * 32;
+  const int r = threadIdx.x >> 3, unit = threadIdx.x & 7;
+  const int row = row0 + r;
+  float v[4];
+  if (TRANSPOSE) {
+    __shared__ float tile[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kc * KC + w * 4 + j, c = row0 + lane;            // source row k, source column c
+      tile[w * 4 + j][lane] = (k < src_rows && c < src_cols) ? src[(int64_t)k * src_ld + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = tile[unit * 4 + e][r];
+  } else {
+    const int k = kc * KC + unit * 4;
+    const float* p = src + (int64_t)row * src_ld + k;
+    if (row < src_rows && k + 3 < src_cols && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4 q = *reinterpret_cast<const float4*>(p);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = (row < src_rows && k + e < src_cols) ? p[e] : 0.0f;
+    }
+  }
+  if (row >= rows_pad) return;
+  float hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
+  const int rt = row / tile_rows, rr = row - rt * tile_rows;
+  const int tiles = rows_pad / tile_rows;
+  const int64_t off = (((int64_t)kc * tiles + rt) * tile_rows + rr) * 32 + ((unit ^ (rr & 7)) << 2);
+  const int64_t term_stride = (int64_t)k_chunks * rows_pad * 32;
+  *reinterpret_cast<float4*>(out + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(out + term_stride + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+struct Params {
+  const float* a;        // packed A image (tile_rows = 128)
+  const float* b;        // packed B image (tile_rows = 256)
+  float* c;              // [M][ldc] fp32, accumulated into (caller zeroes it)
+  int64_t M, N, ldc;     // logical sizes (rows beyond M / columns beyond N are dropped)
+  int64_t m_tiles, n_tiles, k_chunks;
+  int32_t splits;        // K splits (gridDim.z)
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_tf32x3(const __grid_constant__ Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (sptr(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_full;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t mt = blockIdx.x, nt = blockIdx.y;
+  // K range of this split
+  const int64_t per = (P.k_chunks + P.splits - 1) / P.splits;
+  const int64_t k0 = (int64_t)blockIdx.z * per;
+  const int64_t k1 = (k0 + per < P.k_chunks) ? k0 + per : P.k_chunks;
+  const int64_t nk = k1 - k0;   // may be <= 0 for a trailing split: then the CTA only participates in setup
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&s_tmem)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (nk > 0) {
+    const int64_t a_term = P.k_chunks * P.m_tiles * (TM * 32);   // floats between the hi and lo images
+    const int64_t b_term = P.k_chunks * P.n_tiles * (TN * 32);
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int64_t i = 0; i < nk; ++i) {
+          const int s = (int)(i % STAGES);
+          mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+          const int64_t kc = k0 + i;
+          const float* a_hi = P.a + (kc * P.m_tiles + mt) * (TM * 32);
+          const float* b_hi = P.b + (kc * P.n_tiles + nt) * (TN * 32);
+          uint8_t* st = smem + (size_t)s * STAGE;
+          mbar_expect_tx(&full[s], STAGE);
+          bulk_g2s(st, a_hi, A_TILE, &full[s]);
+          bulk_g2s(st + A_TILE, a_hi + a_term, A_TILE, &full[s]);
+          bulk_g2s(st + 2 * A_TILE, b_hi, B_TILE, &full[s]);
+          bulk_g2s(st + 2 * A_TILE + B_TILE, b_hi + b_term, B_TILE, &full[s]);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        for (int64_t i = 0; i < nk; ++i) {
+          const int s = (int)(i % STAGES);
+          mbar_wait(&full[s], (i / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t base = sptr(smem + (size_t)s * STAGE);
+          const uint32_t a_hi = base, a_lo = base + A_TILE, b_hi = base + 2 * A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t o = ks * 32;
+            tc_mma_tf32(tmem, make_desc(a_lo + o), make_desc(b_hi + o), IDESC, (i | ks) ? 1u : 0u);   // small terms first
+            tc_mma_tf32(tmem, make_desc(a_hi + o), make_desc(b_lo + o), IDESC, 1u);
+            tc_mma_tf32(tmem, make_desc(a_hi + o), make_desc(b_hi + o), IDESC, 1u);
+          }
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&acc_full);
+      }
+    } else if (warp >= 3) {
+      // ------------------------------- epilogue -------------------------------
+      const int wq = warp & 3;                          // TMEM lane quarter (warps 3..6 -> 3,0,1,2)
+      mbar_wait(&acc_full, 0);
+      tc_fence_after();
+      uint8_t* stg = smem + (size_t)wq * 4096;          // pipeline SMEM is idle now: 32 rows x 128 B per warp
+      const int64_t row0 = mt * TM + wq * 32;
+      const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16);
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        tc_ld16(tbase + c0, v0);
+        tc_ld16(tbase + c0 + 16, v1);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+              make_uint4(v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) =
+              make_uint4(v1[4 * g], v1[4 * g + 1], v1[4 * g + 2], v1[4 * g + 3]);
+        }
+        __syncwarp();
+        const int64_t col0 = nt * TN + c0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int off = (i * 32 + lane) * 16;
+          const int row = off >> 7, unit = (off >> 4) & 7;
+          const int64_t m = row0 + row, n = col0 + unit * 4;
+          if (m < P.M && n + 3 < P.N) {
+            const float4 x = *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+            red_add_v4(P.c + m * P.ldc + n, x);
+          } else if (m < P.M && n < P.N) {
+            const float* x = reinterpret_cast<const float*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+            for (int e = 0; e < 4 && n + e < P.N; ++e) atomicAdd(P.c + m * P.ldc + n + e, x[e]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  }
+}
+
+}  // namespace gemm
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" int64_t b2rl_gemm_packed_floats(int64_t rows, int64_t k, int32_t b_role) {
+  const int64_t tr = b_role ? gemm::TN : gemm::TM;
+  const int64_t rows_pad = (rows + tr - 1) / tr * tr, kc = (k + gemm::KC - 1) / gemm::KC;
+  return 2 * rows_pad * kc * gemm::KC;
+}
+
+extern "C" int b2rl_gemm_split_pack(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
+                                    int32_t transpose, int32_t b_role, float* out_dev, void* stream) {
+  B2RL_REQUIRE(src_dev && out_dev, "null argument");
+  B2RL_REQUIRE(src_rows >= 1 && src_cols >= 1 && src_ld >= src_cols, "bad shape");
+  B2RL_REQUIRE(((uintptr_t)out_dev % 16) == 0, "packed operand must be 16-byte aligned");
+  const int64_t rows = transpose ? src_cols : src_rows, k = transpose ? src_rows : src_cols;
+  const int tr = b_role ? gemm::TN : gemm::TM;
+  const int64_t rows_pad = (rows + tr - 1) / tr * tr, kc = (k + gemm::KC - 1) / gemm::KC;
+  B2RL_REQUIRE(rows_pad < (1 << 30) && kc <= 65535, "operand too large");
+  dim3 grid((unsigned)(rows_pad / 32), (unsigned)kc);
+  if (transpose)
+    gemm::k_split_pack<true><<<grid, 256, 0, (cudaStream_t)stream>>>(src_dev, (int)src_rows, (int)src_cols, src_ld, tr,
+                                                                     out_dev, (int)rows_pad, (int)kc);
+  else
+    gemm::k_split_pack<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src_dev, (int)src_rows, (int)src_cols, src_ld, tr,
+                                                                      out_dev, (int)rows_pad, (int)kc);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed_dev, float* c_dev, int64_t M,
+                                int64_t N, int64_t K, int64_t ldc, int32_t zero_c, void* stream) {
+  B2RL_REQUIRE(a_packed_dev && b_packed_dev && c_dev, "null argument");
+  B2RL_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N, "bad shape");
+  B2RL_REQUIRE(((uintptr_t)c_dev % 16) == 0 && (ldc % 4) == 0, "C must be 16-byte aligned with ldc % 4 == 0");
+  int dev = 0;
+  B2RL_CUDA(cudaGetDevice(&dev));
+  static int sms[64] = {0};
+  static bool attr[64] = {false};
+  const size_t smem_bytes = (size_t)gemm::STAGES * gemm::STAGE + 1024;
+  if (!attr[dev & 63]) {
+    B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    B2RL_CUDA(cudaFuncSetAttribute(gemm::k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    attr[dev & 63] = true;
+  }
+  gemm::Params P{};
+  P.a = a_packed_dev; P.b = b_packed_dev; P.c = c_dev;
+  P.M = M; P.N = N; P.ldc = ldc;
+  P.m_tiles = (M + gemm::TM - 1) / gemm::TM;
+  P.n_tiles = (N + gemm::TN - 1) / gemm::TN;
+  P.k_chunks = (K + gemm::KC - 1) / gemm::KC;
+  // split K until the grid covers the SMs about once (deterministic function of the shape)
+  const int64_t tiles = P.m_tiles * P.n_tiles;
+  int64_t splits = sms[dev & 63] / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  if (splits > P.k_chunks) splits = P.k_chunks;
+  P.splits = (int32_t)splits;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_c) B2RL_CUDA(cudaMemsetAsync(c_dev, 0, (size_t)M * (size_t)ldc * sizeof(float), st));
+  dim3 grid((unsigned)P.m_tiles, (unsigned)P.n_tiles, (unsigned)splits);
+  gemm::k_gemm_tf32x3<<<grid, gemm::THREADS, smem_bytes, st>>>(P);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}

@@ -230,6 +230,18 @@ int b2rl_rmsprop_step(float* const* params, float* const* grads, float* const* s
                       double eps, int32_t centered, double* sumsq_scratch_dev, float* grad_norm_out_dev,
                       void* stream);
 
+/* The dense heads of the networks (nn.Linear, bias-free: baseline/baseNetwork.py:77-79; 3136 -> 512
+ * adv/val heads cfg/ape_x.json:52-71) at fp32 accuracy on the tensor cores: every fp32 operand is
+ * split into two TF32 terms and C (+)= A[M][K] * B[N][K]^T is formed from three tcgen05 products
+ * with fp32 accumulation.  `split_pack` turns a row-major fp32 matrix (or its transpose) into the
+ * operand image (b_role = 0: the A / M side, 1: the B / N side); `packed_floats` is the size of
+ * that image in floats.  C is accumulated into by K-split partial tiles; zero_c clears it first. */
+int64_t b2rl_gemm_packed_floats(int64_t rows, int64_t k, int32_t b_role);
+int b2rl_gemm_split_pack(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
+                         int32_t transpose, int32_t b_role, float* out_dev, void* stream);
+int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed_dev, float* c_dev, int64_t M,
+                     int64_t N, int64_t K, int64_t ldc, int32_t zero_c, void* stream);
+
 /* Number of kernels this library has launched in this process (bench.py's
  * `gpu_launches`). */
 int64_t b2rl_launch_count(void);

@@ -1,0 +1,80 @@
+"""3xTF32 dense layer (csrc/gemm.cu, tcgen05 kind::tf32) against an fp64 matmul of the same inputs.
+Floating-point kernel -> tolerance, stated per assert: the error must be of the order of an fp32
+FMA chain (the cuBLAS fp32 SIMT GEMM the reference's nn.Linear runs as), far below plain TF32."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributed_rl_b200 import linear
+    return linear
+
+
+def _rel(a, ref):
+    return ((a.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 1024, 3136), (512, 512, 3136), (1, 6, 512), (37, 19, 100), (130, 300, 33),
+                                   (512, 3136, 1024), (1024, 3136, 512)])
+def test_forward_matches_fp64(L, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    x[0, 0] = 1e4                                      # wide dynamic range within a row
+    ref = x.double() @ w.double().T
+    y = L.linear3x(x, w)
+    assert y.shape == (M, N)
+    e3, e32 = _rel(y, ref), _rel(x @ w.T, ref)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        e_tf32 = _rel(x @ w.T, ref)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert e3 < 5e-6, (e3, e32, e_tf32)                # fp32-class accuracy
+    assert e3 < 4 * e32 + 5e-7, (e3, e32, e_tf32)      # per-product error 2^-22 (dropped lo*lo, TF32-truncated lo) + tensor-core accumulation
+    if K >= 512 and M > 1:
+        assert e3 < e_tf32 / 20, (e3, e32, e_tf32)     # ... and far from what plain TF32 gives
+
+
+def test_backward_matches_fp64(L):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(512, 3136, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(1024, 3136, device="cuda", generator=g) * 0.02).requires_grad_()
+    gy = torch.randn(512, 1024, device="cuda", generator=g)
+    L.linear3x(x, w).backward(gy)
+    gx_ref = gy.double() @ w.detach().double()
+    gw_ref = gy.double().T @ x.detach().double()
+    assert _rel(x.grad, gx_ref) < 5e-6
+    assert _rel(w.grad, gw_ref) < 5e-6
+
+
+def test_odd_shapes_backward(L):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(37, 100, device="cuda", generator=g, requires_grad=True)
+    w = torch.randn(19, 100, device="cuda", generator=g, requires_grad=True)
+    y = L.linear3x(x, w)
+    y.square().sum().backward()
+    xr = x.detach().double().requires_grad_()
+    wr = w.detach().double().requires_grad_()
+    (xr @ wr.T).square().sum().backward()
+    assert _rel(y, (xr @ wr.T).detach()) < 5e-6
+    assert _rel(x.grad, xr.grad) < 5e-6
+    assert _rel(w.grad, wr.grad) < 5e-6
+
+
+def test_special_values_do_not_leak(L):
+    x = torch.zeros(4, 32, device="cuda")
+    w = torch.zeros(8, 32, device="cuda")
+    x[1, 3] = float("inf")
+    w[2, 3] = 1.0
+    x[2, 5] = 3e-39                                    # subnormal input: flushed or kept, never NaN
+    w[:, 5] = 1.0
+    y = L.linear3x(x, w)
+    assert not torch.isfinite(y[1, 2])                 # inf input: non-finite output (inf*0 of the lo term -> NaN)
+    assert torch.isfinite(y[0]).all() and torch.isfinite(y[2]).all() and torch.isfinite(y[3]).all()
