@@ -18,6 +18,8 @@ All layers are bias-free, as in the reference (baseNetwork.py:77-79,165-172).
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -190,6 +192,7 @@ class GraphAgent(nn.Module):
         # share the input, so they run as ONE GEMM on the concatenated weights (same maths, wider N).
         self.fuse_sibling_heads = True
         self.dense_3xtf32 = False       # first Linear of fused sibling heads via linear.linear3x (csrc/gemm.cu)
+        self._pack_cache = None         # see packed_heads_cache()
         groups = {}
         for name in order:
             m = getattr(self, name)
@@ -214,7 +217,8 @@ class GraphAgent(nn.Module):
                     ws = [next(iter(getattr(self, n).children())).weight for n in group]
                     if self.dense_3xtf32 and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32:
                         from .linear import linear3x
-                        h = linear3x(x, torch.cat(ws, 0))
+                        cache = None if self._pack_cache is None else self._pack_cache.setdefault(group, {})
+                        h = linear3x(x, ws, cache)
                     else:
                         h = torch.nn.functional.linear(x, torch.cat(ws, 0))
                     for n, part in zip(group, torch.split(h, [w.shape[0] for w in ws], dim=-1)):
@@ -224,6 +228,16 @@ class GraphAgent(nn.Module):
             srcs = [inputs[i] for i in self._ext[name]] + [vals[p] for p in self._prev[name]]
             vals[name] = getattr(self, name)(tuple(srcs))
         return tuple(vals[n] for n in self._outputs)
+
+    @contextlib.contextmanager
+    def packed_heads_cache(self):
+        """While active, the packed (3xTF32) forward operand of the fused heads is built once and reused by
+        every forward pass: use it around several passes between which the weights do not change."""
+        self._pack_cache = {}
+        try:
+            yield
+        finally:
+            self._pack_cache = None
 
     def first_conv_node(self):
         """Name of the CNN2D node fed by external input 0, if it starts with the Atari conv_1."""

@@ -139,15 +139,39 @@ class Replay(threading.Thread):
             return
         recs = [pickle.loads(b) for b in blobs]
         n = len(recs)
-        s = np.stack([np.asarray(r[0], np.uint8) for r in recs])
-        ns = np.stack([np.asarray(r[3], np.uint8) for r in recs])
-        a = np.asarray([int(r[1]) for r in recs], np.int32)
-        rw = np.asarray([float(r[2]) for r in recs], np.float32)
-        d = np.asarray([bool(r[4]) for r in recs], np.uint8)
-        p = np.asarray([float(r[5]) for r in recs], np.float32)
+        st = self._staging(n)        # pinned, on the GPU's NUMA node: the H2D copy is a straight DMA
+        s, ns, a, rw, d, p = (st[k][:n].numpy() for k in ("s", "ns", "a", "r", "d", "p"))
+        for i, r in enumerate(recs):
+            s[i] = np.asarray(r[0], np.uint8).reshape(s.shape[1:])
+            ns[i] = np.asarray(r[3], np.uint8).reshape(ns.shape[1:])
+            a[i], rw[i], d[i], p[i] = int(r[1]), float(r[2]), bool(r[4]), float(r[5])
         with self._lock:
-            self.store.push([s, ns, a, rw, d], p)
+            self.store.push([st[k][:n] for k in ("s", "ns", "a", "r", "d")], st["p"][:n])
+            st["event"].record(torch.cuda.current_stream(self.device))
         self.total_frame += n
+
+    def _staging(self, n: int) -> dict:
+        """One of two pinned staging sets (alternating), grown on demand; reused only after the copy that
+        last read it has completed."""
+        from .hostmem import pinned_empty
+        if not hasattr(self, "_stages"):
+            self._stages, self._stage_i = [None, None], 0
+        self._stage_i ^= 1
+        st = self._stages[self._stage_i]
+        if st is not None:
+            st["event"].synchronize()
+        if st is None or st["cap"] < n:
+            cap = max(n, 2 * (st["cap"] if st else 0), 64)
+            shape = tuple(self.store.fields[0].shape)
+            st = {"cap": cap, "event": torch.cuda.Event(),
+                  "s": pinned_empty((cap, *shape), torch.uint8, self.device),
+                  "ns": pinned_empty((cap, *shape), torch.uint8, self.device),
+                  "a": pinned_empty((cap,), torch.int32, self.device),
+                  "r": pinned_empty((cap,), torch.float32, self.device),
+                  "d": pinned_empty((cap,), torch.uint8, self.device),
+                  "p": pinned_empty((cap,), torch.float32, self.device)}
+            self._stages[self._stage_i] = st
+        return st
 
     def push_arrays(self, s, ns, a, r, d, p) -> None:
         """Same ingest for already-decoded arrays (host pinned or device)."""
@@ -219,7 +243,10 @@ class _Conv1Gathered(torch.autograd.Function):
     """conv_1 over rows `idx` of a uint8 frame table (a replay field or an explicit batch).
     Forward: fused gather+conv on the tensor cores (or a precomputed output of the same kernel).
     Backward: only dL/dW is needed (the input is data); cuDNN computes it from a gathered fp32
-    copy of the same rows — the one place the sampled frames are staged."""
+    copy of the same rows — the one place the sampled frames are staged — or, with `fused_wgrad`
+    (default), libb2rl's fused gather + wgrad kernel computes it from the uint8 rows directly."""
+
+    fused_wgrad = True
 
     @staticmethod
     def forward(ctx, weight, frames, idx, pack, mem_format, store=None, y_pre=None):
@@ -233,6 +260,10 @@ class _Conv1Gathered(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         (idx,) = ctx.saved_tensors
+        if _Conv1Gathered.fused_wgrad:
+            # fused gather + wgrad on the tensor cores: the sampled rows are never staged (csrc/conv1_wgrad.cu)
+            gw = R.conv1_wgrad(ctx.frames, idx if ctx.has_idx else None, gy)
+            return gw, None, None, None, None, None, None
         if not ctx.has_idx:
             x = ctx.frames
         elif ctx.store is not None:    # TMA bulk gather straight from the replay payload
@@ -370,12 +401,13 @@ class Learner:
         self._pack1.pack(0, w_on)
         self._pack2.pack(0, w_on)
         self._pack2.pack(1, w_tg)
-        with torch.no_grad():
-            y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
-            qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
-            qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
-        y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
-        q = self.model.forward_from_conv1(y, False)[0]                       # :78
+        with self.model.packed_heads_cache():     # the online weights are packed once for both passes
+            with torch.no_grad():
+                y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
+                qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
+                qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
+            y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
+            q = self.model.forward_from_conv1(y, False)[0]                       # :78
         notdone = 1.0 - done.to(torch.float32)
         out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
                             self.gamma_n, self.cfg.ALPHA)

@@ -1,0 +1,413 @@
+// Fused gather + weight gradient of the first convolution on the 5th-gen tensor cores.
+//
+//   dW[co, c, ky, kx] = (1/255) * sum_{k, oy, ox} gy[k, oy, ox, co] * frame[idx[k]][c, 4oy+ky, 4ox+kx]
+//
+// the backward half of csrc/conv1.cu (baseline/baseNetwork.py:165-172; loss.backward() of
+// APE_X/Learner.py:123-138).  The input of conv_1 is data, so only dL/dW is needed.  The unfused
+// path gathers the sampled uint8 rows, converts them to fp32 NHWC (58 MB for a batch of 512) and runs
+// cuDNN's fp32 wgrad; here the sampled rows go HBM -> SMEM (TMA bulk copy) -> transposed im2col
+// (patch element x output position, uint8) -> tcgen05.mma -> TMEM, and are never staged in HBM.
+//
+// Arithmetic: the GEMM is D[e = (c,ky,kx)][co] = sum_p A[e][p] * G[co][p] with p = (k, oy, ox).
+// A holds exact uint8 pixels, so the MMA runs in kind::i8.  The fp32 output gradient is written as
+// four signed 7-bit digits against a per-(CTA, channel) power-of-two scale,
+//     gy = s * (q0 + q1/2^7 + q2/2^14 + q3/2^21)     (exact for |gy| >= s*2^-3, else +- s*2^-22),
+// the digits being four groups of C_OUT rows of the B operand (N = 4*C_OUT).  Integer accumulation over
+// all of the CTA's frame stacks is exact; the epilogue recombines the digit sums in int64 and scales
+// once, so every CTA partial is the exact sum of pixel x (28-bit fixed-point gy).  Partials of the
+// CTAs are summed in fp64 by k_conv1_wgrad_reduce (deterministic, no atomics).
+//
+// Warp roles per CTA (persistent, one CTA per SM, 20 warps):
+//   warp 0        TMA loader: one 28 224-byte frame stack per item
+//   warp 1        MMA issuer (one elected thread): 2 x tcgen05.mma (M = 128 each) per 32-position K step
+//   warp 2        TMEM allocator
+//   warps 4-11    A producers: SMEM frame -> [256 patch elements][128 positions] uint8, K-major SW128
+//   warps 12-19   B producers: gy (NHWC fp32, global) -> digits -> [4*C_OUT][128 positions] int8
+//                 (warp = 8 channels x half of a chunk's 16-position units)
+//   warps 16-19   then run the epilogue once: TMEM -> int64 recombination -> partial[cta][co][e]
+#include "common.cuh"
+
+namespace b2rl {
+namespace conv1w {
+
+constexpr int C_IN = 4, HW = 84, KS = 8, STRIDE = 4, OHW = 20;
+constexpr int E_TOTAL = C_IN * KS * KS;            // 256 patch elements = GEMM M (two halves of 128)
+constexpr int FRAME_BYTES = C_IN * HW * HW;        // 28 224
+constexpr int RAW_STRIDE = 28288;
+constexpr int POS = OHW * OHW;                     // 400 output positions per frame stack
+constexpr int NSPLIT = 4;
+constexpr int KCHUNK = 128;                        // positions per pipeline stage (one 128-byte K row)
+constexpr int CHUNKS = 4;                          // 128 + 128 + 128 + 16 (+16 zero padding)
+constexpr int A_BYTES = E_TOTAL * KCHUNK;          // 32 KiB
+constexpr int STAGES = 3;
+constexpr int THREADS = 640;
+constexpr int A_PRODUCERS = 256, B_PRODUCERS = 256;
+constexpr int MAX_ITEMS_PER_CTA = 160;             // int32 accumulators: 127*255*400*T < 2^31
+
+__device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(c));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(sptr(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   sptr(dst)), "l"(src), "r"(bytes), "r"(sptr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc),
+      "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// K-major SW128 descriptor and u8 x s8 -> s32 instruction descriptor: see csrc/conv1.cu
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// byte offset of (row, 16-byte unit) in a one-chunk K-major SW128 operand
+__device__ __forceinline__ int sw_row(int row) { return (row >> 3) * 1024 + (row & 7) * 128; }
+
+struct Params {
+  const uint8_t* frames;     // field base: rows of FRAME_BYTES
+  const int64_t* idx;        // sampled rows, or nullptr for rows 0..n-1
+  int64_t n, capacity;
+  const float* gy;           // [n][400][C_OUT] fp32 (NHWC)
+  float* partial;            // [gridDim.x][C_OUT][256]
+};
+
+template <int C_OUT>
+__global__ void __launch_bounds__(THREADS, 1)
+k_conv1_wgrad(const __grid_constant__ Params P) {
+  constexpr int N_TOTAL = NSPLIT * C_OUT;              // 128 (64 for 16 channels)
+  constexpr int B_BYTES = N_TOTAL * KCHUNK;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * N_TOTAL;          // two M halves
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (sptr(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sStage = smem;
+  uint8_t* sRaw = smem + STAGES * STAGE_BYTES;
+  __shared__ __align__(8) uint64_t raw_full[2], raw_empty[2], s_full[STAGES], s_empty[STAGES], acc_full;
+  __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_absmax[32];                    // per channel: bits of max |gy| over this CTA's items
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) s_absmax[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], A_PRODUCERS); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], A_PRODUCERS + B_PRODUCERS); mbar_init(&s_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&s_tmem)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------ TMA loader ------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t k = first; k < P.n; k += stride, ++it) {
+        const int s = it & 1;
+        mbar_wait(&raw_empty[s], ((it >> 1) & 1) ^ 1);
+        int64_t row = P.idx ? P.idx[k] : k;
+        row = row < 0 ? 0 : (row >= P.capacity ? P.capacity - 1 : row);
+        mbar_expect_tx(&raw_full[s], FRAME_BYTES);
+        bulk_g2s(sRaw + s * RAW_STRIDE, P.frames + row * FRAME_BYTES, FRAME_BYTES, &raw_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(N_TOTAL);
+      int at = 0;
+      uint32_t started = 0;
+      for (int64_t k = first; k < P.n; k += stride) {
+        for (int j = 0; j < CHUNKS; ++j, ++at) {
+          const int stage = at % STAGES;
+          mbar_wait(&s_full[stage], (at / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = sptr(sStage + stage * STAGE_BYTES), b_base = a_base + A_BYTES;
+          const int ksteps = (j < CHUNKS - 1) ? 4 : 1;   // last chunk: positions 384..399 (+16 zeros)
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t bd = make_desc(b_base + ks * 32);
+            tc_mma_i8(tmem, make_desc(a_base + ks * 32), bd, idesc, started);
+            tc_mma_i8(tmem + N_TOTAL, make_desc(a_base + 128 * 128 + ks * 32), bd, idesc, started);
+            started = 1u;
+          }
+          tc_commit(&s_empty[stage]);
+        }
+      }
+      tc_commit(&acc_full);
+    }
+  } else if (warp >= 4) {
+    // -------- all producers first find max |gy| per channel over this CTA's items (the digit scale) --------
+    {
+      const int pt = threadIdx.x - 128;                 // 0..511
+      const int co = pt % C_OUT;
+      uint32_t m = 0u;
+      for (int64_t k = first; k < P.n; k += stride) {
+        const float* g = P.gy + k * (int64_t)(POS * C_OUT);
+#pragma unroll 5
+        for (int e = pt; e < POS * C_OUT; e += 512) m = max(m, __float_as_uint(g[e]) & 0x7FFFFFFFu);   // 512 % C_OUT == 0
+      }
+      atomicMax(&s_absmax[co], m);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    if (warp < 12) {
+      // ------------------- A producers: transposed im2col, uint8 -------------------
+      const int aw = warp - 4;
+      int at = 0, it = 0;
+      for (int64_t k = first; k < P.n; k += stride, ++it) {
+        const int s = it & 1;
+        mbar_wait(&raw_full[s], (it >> 1) & 1);
+        const uint8_t* raw = sRaw + s * RAW_STRIDE;
+        for (int j = 0; j < CHUNKS; ++j, ++at) {
+          const int stage = at % STAGES;
+          mbar_wait(&s_empty[stage], ((at / STAGES) & 1) ^ 1);
+          const int p0 = j * KCHUNK + 4 * lane;          // this lane's 4 consecutive positions (same oy: 20 % 4 == 0)
+          if (p0 < POS) {
+            const int oy = p0 / OHW, ox0 = p0 - oy * OHW;
+            const uint8_t* src0 = raw + (STRIDE * oy) * HW + STRIDE * ox0;
+            uint8_t* dstA = sStage + stage * STAGE_BYTES;
+            const int unit = lane >> 2, word = (lane & 3) * 4;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int eq = aw * 8 + r;                 // (c, ky, kx half): 64 quads of 4 patch elements
+              const int c = eq >> 4, ky = (eq >> 1) & 7, kxh = eq & 1;
+              const uint32_t* src = reinterpret_cast<const uint32_t*>(src0 + c * (HW * HW) + ky * HW + 4 * kxh);
+              const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];   // pixels of positions p0..p0+3
+              const int e0 = c * 64 + ky * 8 + 4 * kxh;
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) {
+                const uint32_t sel = (uint32_t)(kx | ((4 + kx) << 4));
+                const uint32_t t01 = __byte_perm(w0, w1, sel), t23 = __byte_perm(w2, w3, sel);
+                const int e = e0 + kx;
+                *reinterpret_cast<uint32_t*>(dstA + sw_row(e) + ((unit ^ (e & 7)) << 4) + word) =
+                    __byte_perm(t01, t23, 0x5410);
+              }
+            }
+          }
+          fence_async_smem();
+          mbar_arrive(&s_full[stage]);
+        }
+        mbar_arrive(&raw_empty[s]);
+      }
+    } else {
+      // ------------------- B producers: gy -> four signed 7-bit digits -------------------
+      const int bw = (warp - 12) & 3, uh = (warp - 12) >> 2;      // channel group, half of the chunk's units
+      const int c3 = lane & 7, pq = lane >> 3;
+      const int co = 8 * bw + c3;
+      const bool active = (8 * bw) < C_OUT;
+      float inv_s = 1.0f;
+      if (active) {
+        const float t = __uint_as_float(s_absmax[co]) / 127.0f;
+        int e = (int)((__float_as_uint(t) >> 23) & 0xFF) + 1;     // s = 2^(e-127) > t
+        e = e < 27 ? 27 : (e > 227 ? 227 : e);
+        inv_s = __uint_as_float((uint32_t)(254 - e) << 23);
+      }
+      int at = 0;
+      for (int64_t k = first; k < P.n; k += stride) {
+        const float* g = P.gy + k * (int64_t)(POS * C_OUT) + co;
+        for (int j = 0; j < CHUNKS; ++j, ++at) {
+          const int stage = at % STAGES;
+          // this warp's units of the chunk: 4 of 8 (last chunk: unit 0 = positions 384..399, unit 1 = zeros)
+          const int u0 = (j < CHUNKS - 1) ? uh * 4 : uh, nu = (j < CHUNKS - 1) ? 4 : 1;
+          float v[4][4];
+          if (active) {                                            // all loads of the chunk in flight before the wait
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              const int p = j * KCHUNK + (u0 + uu) * 16 + 4 * pq;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[uu][i] = (uu < nu && p < POS) ? g[(int64_t)(p + i) * C_OUT] : 0.0f;
+            }
+          }
+          mbar_wait(&s_empty[stage], ((at / STAGES) & 1) ^ 1);
+          if (active) {
+            uint8_t* dstB = sStage + stage * STAGE_BYTES + A_BYTES;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              if (uu >= nu) break;
+              uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float x = v[uu][i] * inv_s;                        // exact: power-of-two scale, |x| <= 127
+                int q0 = __float2int_rn(x);
+                q0 = max(-127, min(127, q0));
+                x = (x - (float)q0) * 128.0f;                       // exact
+                const int q1 = __float2int_rn(x);
+                x = (x - (float)q1) * 128.0f;
+                const int q2 = __float2int_rn(x);
+                x = (x - (float)q2) * 128.0f;
+                int q3 = __float2int_rn(x);
+                q3 = max(-127, min(127, q3));
+                d0 |= (uint32_t)(q0 & 0xFF) << (8 * i);
+                d1 |= (uint32_t)(q1 & 0xFF) << (8 * i);
+                d2 |= (uint32_t)(q2 & 0xFF) << (8 * i);
+                d3 |= (uint32_t)(q3 & 0xFF) << (8 * i);
+              }
+              const int off = (((u0 + uu) ^ c3) << 4) + pq * 4;    // rows d*C_OUT + co: (row & 7) == c3
+              *reinterpret_cast<uint32_t*>(dstB + sw_row(0 * C_OUT + co) + off) = d0;
+              *reinterpret_cast<uint32_t*>(dstB + sw_row(1 * C_OUT + co) + off) = d1;
+              *reinterpret_cast<uint32_t*>(dstB + sw_row(2 * C_OUT + co) + off) = d2;
+              *reinterpret_cast<uint32_t*>(dstB + sw_row(3 * C_OUT + co) + off) = d3;
+            }
+          }
+          fence_async_smem();
+          mbar_arrive(&s_full[stage]);
+        }
+      }
+      if (warp >= 16) {
+        // ------------------------------- epilogue (once) -------------------------------
+        const int wq = warp & 3;
+        mbar_wait(&acc_full, 0);
+        tc_fence_after();
+        float* out = P.partial + (int64_t)blockIdx.x * (C_OUT * E_TOTAL);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int e = h * 128 + wq * 32 + lane;
+          const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(h * N_TOTAL);
+#pragma unroll 1
+          for (int cg = 0; cg < C_OUT / 16; ++cg) {
+            int32_t q0[16], q1[16], q2[16], q3[16];
+            tc_ld16(tbase + 0 * C_OUT + cg * 16, q0);
+            tc_ld16(tbase + 1 * C_OUT + cg * 16, q1);
+            tc_ld16(tbase + 2 * C_OUT + cg * 16, q2);
+            tc_ld16(tbase + 3 * C_OUT + cg * 16, q3);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int cc = cg * 16 + i;
+              const float t = __uint_as_float(s_absmax[cc]) / 127.0f;
+              int ex = (int)((__float_as_uint(t) >> 23) & 0xFF) + 1;
+              ex = ex < 27 ? 27 : (ex > 227 ? 227 : ex);
+              const double s = (double)__uint_as_float((uint32_t)ex << 23);
+              const long long V = ((long long)q0[i] << 21) + ((long long)q1[i] << 14) + ((long long)q2[i] << 7) + (long long)q3[i];
+              out[cc * E_TOTAL + e] = (float)((double)V * (s * (1.0 / 2097152.0) / 255.0));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+  }
+}
+
+// dW[i] (+)= sum over CTAs of partial[cta][i], accumulated in fp64 in CTA order (deterministic)
+__global__ void __launch_bounds__(256)
+k_conv1_wgrad_reduce(const float* __restrict__ partial, int n_parts, int numel, int accumulate, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  double s = 0.0;
+  for (int p = 0; p < n_parts; ++p) s += (double)partial[(int64_t)p * numel + i];
+  out[i] = accumulate ? (float)((double)out[i] + s) : (float)s;
+}
+
+template <int C_OUT>
+constexpr size_t smem_bytes() {
+  return (size_t)STAGES * (A_BYTES + NSPLIT * C_OUT * KCHUNK) + 2 * (size_t)RAW_STRIDE + 1024;
+}
+
+}  // namespace conv1w
+}  // namespace b2rl
+
+using namespace b2rl;
+
+template <int C_OUT>
+static cudaError_t wgrad_launch(const conv1w::Params& P, unsigned grid, cudaStream_t st) {
+  static bool attr[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr[dev & 63]) {
+    e = cudaFuncSetAttribute(conv1w::k_conv1_wgrad<C_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)conv1w::smem_bytes<C_OUT>());
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  conv1w::k_conv1_wgrad<C_OUT><<<grid, conv1w::THREADS, conv1w::smem_bytes<C_OUT>(), st>>>(P);
+  return cudaSuccess;
+}
+
+extern "C" int64_t b2rl_conv1_wgrad_workspace_floats(int32_t c_out) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return (int64_t)sms * c_out * conv1w::E_TOTAL;
+}
+
+extern "C" int b2rl_conv1_wgrad(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
+                                const float* gy_dev, int32_t c_out, float* workspace_dev, float* gw_dev,
+                                int32_t accumulate, void* stream) {
+  B2RL_REQUIRE(n >= 1, "n must be positive");
+  B2RL_REQUIRE(frames_dev && gy_dev && workspace_dev && gw_dev, "null argument");
+  B2RL_REQUIRE(c_out == 16 || c_out == 32, "c_out must be 16 or 32");
+  B2RL_REQUIRE(capacity >= 1, "capacity must be positive");
+  B2RL_REQUIRE(((uintptr_t)frames_dev % 16 == 0) && ((uintptr_t)gy_dev % 16 == 0), "frames and gy must be 16-byte aligned");
+  int dev = 0;
+  B2RL_CUDA(cudaGetDevice(&dev));
+  static int sms[64] = {0};
+  if (!sms[dev & 63]) B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int numel = c_out * conv1w::E_TOTAL;
+  const int64_t per_launch = (int64_t)sms[dev & 63] * conv1w::MAX_ITEMS_PER_CTA;   // int32 accumulator bound
+  for (int64_t off = 0; off < n; off += per_launch) {
+    const int64_t m = (n - off < per_launch) ? n - off : per_launch;
+    conv1w::Params P{frames_dev, idx_dev ? idx_dev + off : nullptr, m, capacity,
+                     gy_dev + off * (int64_t)(conv1w::POS * c_out), workspace_dev};
+    if (!idx_dev) P.frames = frames_dev + off * conv1w::FRAME_BYTES, P.capacity = capacity - off;
+    const unsigned grid = (unsigned)((m < sms[dev & 63]) ? m : sms[dev & 63]);
+    B2RL_CUDA(c_out == 32 ? wgrad_launch<32>(P, grid, st) : wgrad_launch<16>(P, grid, st));
+    count_launch();
+    B2RL_CHECK_LAUNCH();
+    conv1w::k_conv1_wgrad_reduce<<<(numel + 255) / 256, 256, 0, st>>>(workspace_dev, (int)grid, numel,
+                                                                       (accumulate || off > 0) ? 1 : 0, gw_dev);
+    count_launch();
+    B2RL_CHECK_LAUNCH();
+  }
+  return B2RL_OK;
+}

@@ -11,8 +11,9 @@
 //                  128B-swizzled, K-major tile layout the MMA reads, so the GEMM's loader is a
 //                  plain cp.async.bulk per tile (no tensor map, no SM-side staging)
 //   k_gemm_tf32x3  one CTA per (m-tile 128, n-tile 256, K-split): TMA loader warp, one MMA-issuing
-//                  thread (12 x tcgen05.mma per 32-float K chunk), 4 epilogue warps that add the
-//                  partial tile into C with coalesced vector reductions
+//                  thread (12 x tcgen05.mma per 32-float K chunk), 4 epilogue warps that store the tile
+//                  (or, when K is split, this split's partial tile) with coalesced 512-byte stores
+//   k_splitk_reduce sums the K-split partials in split order: the result is deterministic (no atomics)
 #include "common.cuh"
 
 namespace b2rl {
@@ -65,10 +66,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
-}
 // K-major SW128 descriptor (see csrc/conv1.cu): SBO = 1024 B, LBO = 16 B, version 1, layout SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
@@ -95,7 +92,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 template <bool TRANSPOSE>
 __global__ void __launch_bounds__(256)
 k_split_pack(const float* __restrict__ src, int src_rows, int src_cols, int64_t src_ld, int tile_rows,
-             float* __restrict__ out, int rows_pad, int k_chunks) {
+             float* __restrict__ out, int rows_pad, int k_chunks, int row_off, int kc_off) {
+  // (row, kc) below are local to this piece; the image position is (row_off + row, kc_off + kc)
   const int kc = blockIdx.y, row0 = blockIdx.x * 32;
   const int r = threadIdx.x >> 3, unit = threadIdx.x & 7;
   const int row = row0 + r;
@@ -122,13 +120,14 @@ k_split_pack(const float* __restrict__ src, int src_rows, int src_cols, int64_t 
       for (int e = 0; e < 4; ++e) v[e] = (row < src_rows && k + e < src_cols) ? p[e] : 0.0f;
     }
   }
-  if (row >= rows_pad) return;
+  const int irow = row_off + row, ikc = kc_off + kc;
+  if (irow >= rows_pad) return;
   float hi[4], lo[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
-  const int rt = row / tile_rows, rr = row - rt * tile_rows;
+  const int rt = irow / tile_rows, rr = irow - rt * tile_rows;
   const int tiles = rows_pad / tile_rows;
-  const int64_t off = (((int64_t)kc * tiles + rt) * tile_rows + rr) * 32 + ((unit ^ (rr & 7)) << 2);
+  const int64_t off = (((int64_t)ikc * tiles + rt) * tile_rows + rr) * 32 + ((unit ^ (rr & 7)) << 2);
   const int64_t term_stride = (int64_t)k_chunks * rows_pad * 32;
   *reinterpret_cast<float4*>(out + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<float4*>(out + term_stride + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -137,7 +136,7 @@ k_split_pack(const float* __restrict__ src, int src_rows, int src_cols, int64_t 
 struct Params {
   const float* a;        // packed A image (tile_rows = 128)
   const float* b;        // packed B image (tile_rows = 256)
-  float* c;              // [M][ldc] fp32, accumulated into (caller zeroes it)
+  float* c;              // splits == 1: C [M][ldc] fp32 (stored); else the partials [split][M][ldc]
   int64_t M, N, ldc;     // logical sizes (rows beyond M / columns beyond N are dropped)
   int64_t m_tiles, n_tiles, k_chunks;
   int32_t splits;        // K splits (gridDim.z)
@@ -237,12 +236,13 @@ k_gemm_tf32x3(const __grid_constant__ Params P) {
           const int off = (i * 32 + lane) * 16;
           const int row = off >> 7, unit = (off >> 4) & 7;
           const int64_t m = row0 + row, n = col0 + unit * 4;
+          float* dst = P.c + ((int64_t)blockIdx.z * P.M + m) * P.ldc + n;
           if (m < P.M && n + 3 < P.N) {
-            const float4 x = *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
-            red_add_v4(P.c + m * P.ldc + n, x);
+            *reinterpret_cast<float4*>(dst) =
+                *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
           } else if (m < P.M && n < P.N) {
             const float* x = reinterpret_cast<const float*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
-            for (int e = 0; e < 4 && n + e < P.N; ++e) atomicAdd(P.c + m * P.ldc + n + e, x[e]);
+            for (int e = 0; e < 4 && n + e < P.N; ++e) dst[e] = x[e];
           }
         }
         __syncwarp();
@@ -253,6 +253,31 @@ k_gemm_tf32x3(const __grid_constant__ Params P) {
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  }
+}
+
+// C[i] = sum over splits (in split order: deterministic) of partial[z][i]; one thread per 4 columns
+__global__ void __launch_bounds__(256)
+k_splitk_reduce(const float* __restrict__ partial, int splits, int64_t M, int64_t N, int64_t ldc, float* __restrict__ c) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_row = ldc >> 2;
+  if (q >= M * per_row) return;
+  const int64_t m = q / per_row, n = (q - m * per_row) << 2;
+  if (n >= N) return;
+  const int64_t off = m * ldc + n, stride = M * ldc;
+  if (n + 3 < N) {
+    float4 a = *reinterpret_cast<const float4*>(partial + off);
+    for (int z = 1; z < splits; ++z) {
+      const float4 b = *reinterpret_cast<const float4*>(partial + z * stride + off);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(c + off) = a;
+  } else {
+    for (int e = 0; n + e < N; ++e) {
+      float a = partial[off + e];
+      for (int z = 1; z < splits; ++z) a += partial[z * stride + off + e];
+      c[off + e] = a;
+    }
   }
 }
 
@@ -267,59 +292,108 @@ extern "C" int64_t b2rl_gemm_packed_floats(int64_t rows, int64_t k, int32_t b_ro
   return 2 * rows_pad * kc * gemm::KC;
 }
 
-extern "C" int b2rl_gemm_split_pack(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
-                                    int32_t transpose, int32_t b_role, float* out_dev, void* stream) {
+// One piece of an operand: the piece's rows go to image rows [row_offset, ...), its contraction index to
+// [k_offset, ...) of an operand with total_rows x total_k.  Pieces tile the operand (vertically stacked weight
+// matrices, or their transposes side by side); the piece that ends the operand also writes the zero padding.
+extern "C" int b2rl_gemm_split_pack_into(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
+                                         int32_t transpose, int32_t b_role, float* out_dev, int64_t total_rows,
+                                         int64_t total_k, int64_t row_offset, int64_t k_offset, void* stream) {
   B2RL_REQUIRE(src_dev && out_dev, "null argument");
   B2RL_REQUIRE(src_rows >= 1 && src_cols >= 1 && src_ld >= src_cols, "bad shape");
   B2RL_REQUIRE(((uintptr_t)out_dev % 16) == 0, "packed operand must be 16-byte aligned");
   const int64_t rows = transpose ? src_cols : src_rows, k = transpose ? src_rows : src_cols;
+  B2RL_REQUIRE(row_offset >= 0 && k_offset >= 0 && row_offset + rows <= total_rows && k_offset + k <= total_k,
+               "piece outside the operand");
+  B2RL_REQUIRE(row_offset % 32 == 0 && k_offset % gemm::KC == 0, "piece offsets must be multiples of 32");
+  B2RL_REQUIRE((rows % 32 == 0 || row_offset + rows == total_rows) && (k % gemm::KC == 0 || k_offset + k == total_k),
+               "an inner piece must be a multiple of 32 rows / 32 contraction elements");
   const int tr = b_role ? gemm::TN : gemm::TM;
-  const int64_t rows_pad = (rows + tr - 1) / tr * tr, kc = (k + gemm::KC - 1) / gemm::KC;
-  B2RL_REQUIRE(rows_pad < (1 << 30) && kc <= 65535, "operand too large");
-  dim3 grid((unsigned)(rows_pad / 32), (unsigned)kc);
+  const int64_t rows_pad = (total_rows + tr - 1) / tr * tr, kc_total = (total_k + gemm::KC - 1) / gemm::KC;
+  B2RL_REQUIRE(rows_pad < (1 << 30) && kc_total <= 65535, "operand too large");
+  const int64_t rows_cover = (row_offset + rows == total_rows) ? rows_pad - row_offset : rows;
+  const int64_t kc_cover = (k + gemm::KC - 1) / gemm::KC;
+  dim3 grid((unsigned)(rows_cover / 32), (unsigned)kc_cover);
   if (transpose)
     gemm::k_split_pack<true><<<grid, 256, 0, (cudaStream_t)stream>>>(src_dev, (int)src_rows, (int)src_cols, src_ld, tr,
-                                                                     out_dev, (int)rows_pad, (int)kc);
+                                                                     out_dev, (int)rows_pad, (int)kc_total,
+                                                                     (int)row_offset, (int)(k_offset / gemm::KC));
   else
     gemm::k_split_pack<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src_dev, (int)src_rows, (int)src_cols, src_ld, tr,
-                                                                      out_dev, (int)rows_pad, (int)kc);
+                                                                      out_dev, (int)rows_pad, (int)kc_total,
+                                                                      (int)row_offset, (int)(k_offset / gemm::KC));
   count_launch();
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
 }
 
-extern "C" int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed_dev, float* c_dev, int64_t M,
-                                int64_t N, int64_t K, int64_t ldc, int32_t zero_c, void* stream) {
-  B2RL_REQUIRE(a_packed_dev && b_packed_dev && c_dev, "null argument");
-  B2RL_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N, "bad shape");
-  B2RL_REQUIRE(((uintptr_t)c_dev % 16) == 0 && (ldc % 4) == 0, "C must be 16-byte aligned with ldc % 4 == 0");
+extern "C" int b2rl_gemm_split_pack(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
+                                    int32_t transpose, int32_t b_role, float* out_dev, void* stream) {
+  const int64_t rows = transpose ? src_cols : src_rows, k = transpose ? src_rows : src_cols;
+  return b2rl_gemm_split_pack_into(src_dev, src_rows, src_cols, src_ld, transpose, b_role, out_dev, rows, k, 0, 0, stream);
+}
+
+static int64_t gemm_splits(int64_t M, int64_t N, int64_t K, int sms) {
+  const int64_t tiles = ((M + gemm::TM - 1) / gemm::TM) * ((N + gemm::TN - 1) / gemm::TN);
+  const int64_t kc = (K + gemm::KC - 1) / gemm::KC;
+  int64_t splits = sms / (tiles > 0 ? tiles : 1);      // cover the SMs about once (a function of the shape only)
+  if (splits < 1) splits = 1;
+  if (splits > kc) splits = kc;
+  const int64_t per = (kc + splits - 1) / splits;
+  return (kc + per - 1) / per;                          // no empty trailing split
+}
+
+static int gemm_sms(int* out) {
   int dev = 0;
   B2RL_CUDA(cudaGetDevice(&dev));
   static int sms[64] = {0};
+  if (!sms[dev & 63]) B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  *out = sms[dev & 63];
+  return B2RL_OK;
+}
+
+extern "C" int64_t b2rl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int64_t ldc) {
+  int sms = 0;
+  if (gemm_sms(&sms) != B2RL_OK) return -1;
+  const int64_t splits = gemm_splits(M, N, K, sms);
+  return splits > 1 ? splits * M * ldc : 0;
+}
+
+extern "C" int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed_dev, float* c_dev, int64_t M,
+                                int64_t N, int64_t K, int64_t ldc, float* workspace_dev, void* stream) {
+  B2RL_REQUIRE(a_packed_dev && b_packed_dev && c_dev, "null argument");
+  B2RL_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N, "bad shape");
+  B2RL_REQUIRE(((uintptr_t)c_dev % 16) == 0 && (ldc % 4) == 0, "C must be 16-byte aligned with ldc % 4 == 0");
+  int sms = 0;
+  if (int rc = gemm_sms(&sms)) return rc;
+  int dev = 0;
+  B2RL_CUDA(cudaGetDevice(&dev));
   static bool attr[64] = {false};
   const size_t smem_bytes = (size_t)gemm::STAGES * gemm::STAGE + 1024;
   if (!attr[dev & 63]) {
-    B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
     B2RL_CUDA(cudaFuncSetAttribute(gemm::k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr[dev & 63] = true;
   }
+  const int64_t splits = gemm_splits(M, N, K, sms);
+  B2RL_REQUIRE(splits == 1 || (workspace_dev && ((uintptr_t)workspace_dev % 16) == 0),
+               "this shape splits K: pass b2rl_gemm_workspace_floats() floats of 16-byte aligned workspace");
   gemm::Params P{};
-  P.a = a_packed_dev; P.b = b_packed_dev; P.c = c_dev;
+  P.a = a_packed_dev; P.b = b_packed_dev;
+  P.c = splits > 1 ? workspace_dev : c_dev;
   P.M = M; P.N = N; P.ldc = ldc;
   P.m_tiles = (M + gemm::TM - 1) / gemm::TM;
   P.n_tiles = (N + gemm::TN - 1) / gemm::TN;
   P.k_chunks = (K + gemm::KC - 1) / gemm::KC;
-  // split K until the grid covers the SMs about once (deterministic function of the shape)
-  const int64_t tiles = P.m_tiles * P.n_tiles;
-  int64_t splits = sms[dev & 63] / (tiles > 0 ? tiles : 1);
-  if (splits < 1) splits = 1;
-  if (splits > P.k_chunks) splits = P.k_chunks;
   P.splits = (int32_t)splits;
   cudaStream_t st = (cudaStream_t)stream;
-  if (zero_c) B2RL_CUDA(cudaMemsetAsync(c_dev, 0, (size_t)M * (size_t)ldc * sizeof(float), st));
   dim3 grid((unsigned)P.m_tiles, (unsigned)P.n_tiles, (unsigned)splits);
   gemm::k_gemm_tf32x3<<<grid, gemm::THREADS, smem_bytes, st>>>(P);
   count_launch();
   B2RL_CHECK_LAUNCH();
+  if (splits > 1) {
+    const int64_t quads = M * (ldc >> 2);
+    gemm::k_splitk_reduce<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(workspace_dev, (int)splits, M, N, ldc, c_dev);
+    count_launch();
+    B2RL_CHECK_LAUNCH();
+  }
   return B2RL_OK;
 }

@@ -31,46 +31,79 @@ def split_pack(x: torch.Tensor, transpose: bool, b_role: bool) -> torch.Tensor:
     return out
 
 
-def gemm_packed(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, out: torch.Tensor | None = None,
-                accumulate: bool = False) -> torch.Tensor:
+def gemm_packed(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """C[M][N] = A[M][K] @ B[N][K]^T from packed operand images (A-role, B-role)."""
     if out is None:
         n_pad = (N + 3) // 4 * 4
-        full = torch.empty(M, n_pad, dtype=torch.float32, device=a.device)
-        out = full[:, :N]
-        accumulate = False
+        out = torch.empty(M, n_pad, dtype=torch.float32, device=a.device)[:, :N]
     if out.stride(1) != 1 or out.stride(0) % 4:
         raise ValueError("output rows must be contiguous with a leading dimension divisible by 4")
-    _lib.check(_lib.load().b2rl_gemm_tf32x3(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, out.stride(0),
-                                           0 if accumulate else 1, _stream()))
+    L = _lib.load()
+    n_ws = L.b2rl_gemm_workspace_floats(M, N, K, out.stride(0))
+    ws = torch.empty(n_ws, dtype=torch.float32, device=a.device) if n_ws else None
+    _lib.check(L.b2rl_gemm_tf32x3(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, out.stride(0),
+                                  ws.data_ptr() if ws is not None else None, _stream()))
+    return out
+
+
+def _pack_pieces(mats, transpose: bool, b_role: bool) -> torch.Tensor:
+    """Operand image of vertically stacked matrices (transpose=False: rows stack) or of the transpose of
+    that stack (transpose=True: the pieces sit side by side along the contraction index)."""
+    L = _lib.load()
+    inner, total = mats[0].shape[1], sum(m.shape[0] for m in mats)
+    rows, k = (inner, total) if transpose else (total, inner)
+    out = torch.empty(L.b2rl_gemm_packed_floats(rows, k, int(b_role)), dtype=torch.float32, device=mats[0].device)
+    off = 0
+    for m in mats:
+        if m.stride(1) != 1:
+            m = m.contiguous()
+        _lib.check(L.b2rl_gemm_split_pack_into(m.data_ptr(), m.shape[0], m.shape[1], m.stride(0), int(transpose),
+                                               int(b_role), out.data_ptr(), rows, k,
+                                               0 if transpose else off, off if transpose else 0, _stream()))
+        off += m.shape[0]
     return out
 
 
 class _Linear3x(torch.autograd.Function):
+    """y = x @ cat(ws, 0).T for bias-free layers that share the input (one GEMM; the weights are never
+    concatenated in memory: each is packed into its rows of the operand image).  `cache`: optional dict that
+    keeps the packed forward operand between calls while the caller knows the weights are unchanged."""
+
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, cache, *ws):
         M, K = x.shape
-        N = w.shape[0]
-        y = gemm_packed(split_pack(x, False, False), split_pack(w, False, True), M, N, K)
-        ctx.save_for_backward(x, w)
+        N = sum(w.shape[0] for w in ws)
+        b = cache.get("fwd") if cache is not None else None
+        if b is None:
+            b = _pack_pieces(ws, False, True)
+            if cache is not None:
+                cache["fwd"] = b
+        y = gemm_packed(split_pack(x, False, False), b, M, N, K)
+        ctx.save_for_backward(x, *ws)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
+        x, *ws = ctx.saved_tensors
         M, K = x.shape
-        N = w.shape[0]
+        N = sum(w.shape[0] for w in ws)
         gy = gy.contiguous()
-        gx = gw = None
+        gx, gws = None, [None] * len(ws)
         if ctx.needs_input_grad[0]:
-            # dx[M][K] = gy[M][N] @ w[N][K]: contraction over N, the B operand is w^T ([K rows][N])
-            gx = gemm_packed(split_pack(gy, False, False), split_pack(w, True, True), M, K, N)
-        if ctx.needs_input_grad[1]:
-            # dw[N][K] = gy^T[N][M] @ x[M][K]: contraction over M
+            # dx[M][K] = gy[M][N] @ W[N][K]: contraction over N, the B operand is W^T ([K rows][N])
+            gx = gemm_packed(split_pack(gy, False, False), _pack_pieces(ws, True, True), M, K, N)
+        if any(ctx.needs_input_grad[2:]):
+            # dW[N][K] = gy^T[N][M] @ x[M][K]: contraction over M
             gw = gemm_packed(split_pack(gy, True, False), split_pack(x, True, True), N, K, M)
-        return gx, gw
+            gws = list(torch.split(gw, [w.shape[0] for w in ws], 0))
+        return (gx, None, *gws)
 
 
-def linear3x(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """`torch.nn.functional.linear(x, w)` for 2-D fp32 CUDA `x` ([M][K]) and `w` ([N][K]), bias-free."""
-    return _Linear3x.apply(x, w)
+def linear3x(x: torch.Tensor, w, cache: dict | None = None) -> torch.Tensor:
+    """`torch.nn.functional.linear(x, w)` for 2-D fp32 CUDA `x` ([M][K]) and bias-free `w` ([N][K]); `w` may be
+    a list of weights sharing the input (their outputs are concatenated along the last dimension).  Inner
+    pieces of a list must have a multiple of 32 rows."""
+    ws = [w] if torch.is_tensor(w) else list(w)
+    if len(ws) > 1 and any(m.shape[0] % 32 for m in ws[:-1]):
+        ws = [torch.cat(ws, 0)]
+    return _Linear3x.apply(x, cache, *ws)

@@ -399,3 +399,31 @@ def conv1_fused(frames: torch.Tensor, idx, pack: Conv1Pack, relu: bool = False, 
                                        out.data_ptr(),
                                        int(bool(relu)), _stream_ptr(dev)))
     return [out[i].permute(0, 3, 1, 2) for i in range(pack.n_nets)]   # logical NCHW, physical NHWC
+
+
+_wgrad_ws = {}
+
+
+def conv1_wgrad(frames: torch.Tensor, idx, gy: torch.Tensor, out: torch.Tensor | None = None,
+                accumulate: bool = False) -> torch.Tensor:
+    """dL/dW of conv_1 from the sampled uint8 rows and dL/dy, without staging the rows (b2rl_conv1_wgrad).
+    frames: uint8 (rows, 4, 84, 84) contiguous; idx: int64[n] or None; gy: (n, c_out, 20, 20) fp32
+    (made channels_last if it is not) -> (c_out, 4, 8, 8) fp32."""
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames[0].numel() == FRAME_STACK_BYTES
+    n = frames.shape[0] if idx is None else idx.numel()
+    c_out = gy.shape[1]
+    assert gy.shape == (n, c_out, 20, 20) and gy.dtype == torch.float32
+    gy = gy.contiguous(memory_format=torch.channels_last)
+    dev = frames.device
+    key = (dev, c_out)
+    if key not in _wgrad_ws:
+        _wgrad_ws[key] = torch.empty(_lib.load().b2rl_conv1_wgrad_workspace_floats(c_out), dtype=torch.float32,
+                                     device=dev)
+    if out is None:
+        out = torch.empty((c_out, 4, 8, 8), dtype=torch.float32, device=dev)
+        accumulate = False
+    assert out.is_contiguous() and out.numel() == c_out * 256
+    check(_lib.load().b2rl_conv1_wgrad(frames.data_ptr(), frames.shape[0], None if idx is None else idx.data_ptr(), n,
+                                       gy.data_ptr(), c_out, _wgrad_ws[key].data_ptr(), out.data_ptr(),
+                                       int(bool(accumulate)), _stream_ptr(dev)))
+    return out

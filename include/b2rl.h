@@ -218,6 +218,17 @@ int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t*
                      const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, int32_t c_out,
                      float* out_dev, int32_t relu, void* stream);
 
+/* Weight gradient of conv_1 fused with the gather (the backward half of b2rl_conv1_fused;
+ * loss.backward() in APE_X/Learner.py:123-138 for baseline/baseNetwork.py:165-172's first layer):
+ *   gw[co][c][ky][kx] (+)= (1/255) * sum_{k,oy,ox} gy[k][oy][ox][co] * frames[idx[k]][c][4oy+ky][4ox+kx]
+ * gy_dev: [n][20][20][c_out] fp32 (NHWC); gw_dev: [c_out][4][8][8] fp32; workspace_dev:
+ * b2rl_conv1_wgrad_workspace_floats(c_out) floats of scratch (per-SM partial sums, summed in fp64 in a
+ * fixed order: the result is deterministic).  idx_dev may be NULL (rows 0..n-1). */
+int64_t b2rl_conv1_wgrad_workspace_floats(int32_t c_out);
+int b2rl_conv1_wgrad(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
+                     const float* gy_dev, int32_t c_out, float* workspace_dev, float* gw_dev,
+                     int32_t accumulate, void* stream);
+
 /* Learner.step (APE_X/Learner.py:123-138; IMPALA/Learner.py:258-266 without the clipping) with
  * torch.optim.RMSprop's update (baseline/utils.py getOptim :124-130; centered for Ape-X,
  * cfg/ape_x.json:27-35) in ONE pass: square_avg / grad_avg / param update, gradient zeroed, and
@@ -235,12 +246,20 @@ int b2rl_rmsprop_step(float* const* params, float* const* grads, float* const* s
  * split into two TF32 terms and C (+)= A[M][K] * B[N][K]^T is formed from three tcgen05 products
  * with fp32 accumulation.  `split_pack` turns a row-major fp32 matrix (or its transpose) into the
  * operand image (b_role = 0: the A / M side, 1: the B / N side); `packed_floats` is the size of
- * that image in floats.  C is accumulated into by K-split partial tiles; zero_c clears it first. */
+ * that image in floats.  Shapes with few output tiles split K over the SMs; their partial tiles go to
+ * workspace_dev (b2rl_gemm_workspace_floats floats, 0 = not needed) and are summed in a fixed order,
+ * so the result is deterministic. */
 int64_t b2rl_gemm_packed_floats(int64_t rows, int64_t k, int32_t b_role);
 int b2rl_gemm_split_pack(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
                          int32_t transpose, int32_t b_role, float* out_dev, void* stream);
+/* One piece of an operand (stacked weight matrices): image rows [row_offset, +rows), contraction
+ * [k_offset, +k) of a total_rows x total_k operand; offsets (and inner piece sizes) multiples of 32. */
+int b2rl_gemm_split_pack_into(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
+                              int32_t transpose, int32_t b_role, float* out_dev, int64_t total_rows,
+                              int64_t total_k, int64_t row_offset, int64_t k_offset, void* stream);
+int64_t b2rl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int64_t ldc);
 int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed_dev, float* c_dev, int64_t M,
-                     int64_t N, int64_t K, int64_t ldc, int32_t zero_c, void* stream);
+                     int64_t N, int64_t K, int64_t ldc, float* workspace_dev, void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py's
  * `gpu_launches`). */

@@ -85,3 +85,43 @@ def test_conv1_fused_reads_replay_field_in_place(R):
     want = _ref(frames, w)
     assert (out.cpu().double() - want).abs().max().item() <= 2e-6 * max(want.abs().max().item(), 1.0)
     rep.close()
+
+
+def _wgrad_ref(frames_u8, idx, gy):
+    x = (torch.from_numpy(frames_u8[idx]).double() / 255.0)
+    return torch.nn.grad.conv2d_weight(x, (gy.shape[1], 4, 8, 8), gy.double().cpu(), stride=4)
+
+
+@pytest.mark.parametrize("c_out,n", [(32, 1), (32, 5), (32, 300), (16, 37), (32, 512), (16, 600)])
+def test_conv1_wgrad_matches_fp64(R, c_out, n):
+    """Fused gather + conv_1 weight gradient (csrc/conv1_wgrad.cu) against an fp64 wgrad of the same rows.
+    Tolerance: 2e-6 of the largest |dW| entry (exact integer accumulation of 28-bit fixed-point gy;
+    the only roundings are the digit truncation at 2^-29 of the channel max and the final fp32 store)."""
+    rng = np.random.default_rng(n + c_out)
+    rows = max(n, 8) + 7
+    frames = rng.integers(0, 256, size=(rows, 4, 84, 84), dtype=np.uint8)
+    frames[1] = 255
+    idx = rng.integers(0, rows, size=n)
+    idx[0] = 1
+    g = torch.Generator().manual_seed(n)
+    gy = torch.randn(n, c_out, 20, 20, generator=g) * torch.logspace(-6, 0, n).view(n, 1, 1, 1)   # wide range over items
+    gy[:, 3] = 0.0                                    # an all-zero channel
+    gy[0, 5, 0, 0] = 50.0                             # one dominant entry
+    gy = gy * (torch.rand(n, c_out, 20, 20, generator=g) > 0.5)   # ReLU-masked, like the real dL/dy
+    gyc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    fr = torch.from_numpy(frames).cuda()
+    gw = R.conv1_wgrad(fr, torch.from_numpy(idx).cuda(), gyc)
+    ref = _wgrad_ref(frames, idx, gy)
+    assert gw.shape == (c_out, 4, 8, 8)
+    err = (gw.double().cpu() - ref).abs().max().item()
+    assert err <= 2e-6 * ref.abs().max().item(), (err, ref.abs().max().item())
+    assert (gw[3] == 0).all()
+    # idx=None takes rows 0..n-1; accumulate adds into an existing gradient
+    gw2 = R.conv1_wgrad(fr[:n].contiguous(), None, gyc)
+    ref2 = _wgrad_ref(frames, np.arange(n), gy)
+    assert (gw2.double().cpu() - ref2).abs().max().item() <= 2e-6 * ref2.abs().max().item()
+    acc = gw2.clone()
+    R.conv1_wgrad(fr[:n].contiguous(), None, gyc, out=acc, accumulate=True)
+    torch.testing.assert_close(acc, 2 * gw2, rtol=1e-6, atol=0)
+    # deterministic
+    assert torch.equal(R.conv1_wgrad(fr, torch.from_numpy(idx).cuda(), gyc), gw)

@@ -78,3 +78,26 @@ def test_special_values_do_not_leak(L):
     y = L.linear3x(x, w)
     assert not torch.isfinite(y[1, 2])                 # inf input: non-finite output (inf*0 of the lo term -> NaN)
     assert torch.isfinite(y[0]).all() and torch.isfinite(y[2]).all() and torch.isfinite(y[3]).all()
+
+
+def test_stacked_weights_and_cache(L):
+    """Sibling heads: two weights sharing the input, packed into one operand without a cat; the packed
+    forward operand can be cached across passes; gradients reach each weight."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(64, 3136, device="cuda", generator=g, requires_grad=True)
+    w1 = (torch.randn(512, 3136, device="cuda", generator=g) * 0.02).requires_grad_()
+    w2 = (torch.randn(70, 3136, device="cuda", generator=g) * 0.02).requires_grad_()
+    cache = {}
+    y = L.linear3x(x, [w1, w2], cache)
+    y2 = L.linear3x(x.detach(), [w1, w2], cache)          # served from the cached operand
+    assert torch.equal(y.detach(), y2) and "fwd" in cache
+    ref = x.detach().double() @ torch.cat([w1, w2]).detach().double().T
+    assert _rel(y, ref) < 5e-6
+    gy = torch.randn(64, 582, device="cuda", generator=g)
+    y.backward(gy)
+    assert _rel(x.grad, gy.double() @ torch.cat([w1, w2]).detach().double()) < 5e-6
+    gw = gy.double().T @ x.detach().double()
+    assert _rel(w1.grad, gw[:512]) < 5e-6 and _rel(w2.grad, gw[512:]) < 5e-6
+    # a non-32-multiple inner piece falls back to one concatenated operand
+    y3 = L.linear3x(x.detach(), [w2.detach(), w1.detach()])
+    assert _rel(y3, x.detach().double() @ torch.cat([w2, w1]).detach().double().T) < 5e-6

@@ -413,3 +413,39 @@ def test_async_parameter_publication_and_run_loop(apex):
     assert L._publishers[0].published >= 1 and L._publishers[1].published >= 1
     assert set(pickle.loads(conn.get("target_state_dict"))) == set(L.model.state_dict())
     assert pickle.loads(conn.get("count")) in (0, 50)
+
+
+def test_push_records_decodes_actor_blobs_through_pinned_staging(apex):
+    """Replay.push_records: pickled [s, a, R_n, s', done, prio] records (APE_X/Player.py:252-261) land in the
+    ring in order, through the NUMA-local pinned staging sets (two alternating sets, grown on demand)."""
+    import pickle
+    from distributed_rl_b200 import hostmem
+    cfg, L = _mk(apex, B=32, N=1024, seed=1)
+    rng = np.random.default_rng(0)
+    mem = L.memory
+    recs_all = []
+    for n in (5, 70, 3):                         # second call grows the staging set, third reuses the first
+        recs = [[rng.integers(0, 256, size=(4, 84, 84), dtype=np.uint8), int(rng.integers(0, 6)),
+                 float(rng.standard_normal()), rng.integers(0, 256, size=(4, 84, 84), dtype=np.uint8),
+                 bool(rng.random() < 0.3), float(rng.random() + 0.1)] for _ in range(n)]
+        mem.push_records([pickle.dumps(r) for r in recs])
+        recs_all += recs
+    torch.cuda.synchronize()
+    st = mem.store
+    assert len(st) == 78 and mem.total_frame == 78
+    k = len(recs_all)
+    np.testing.assert_array_equal(st.field_view("state")[:k].cpu().numpy().reshape(k, 4, 84, 84),
+                                  np.stack([r[0] for r in recs_all]))
+    np.testing.assert_array_equal(st.field_view("next_state")[:k].cpu().numpy().reshape(k, 4, 84, 84),
+                                  np.stack([r[3] for r in recs_all]))
+    np.testing.assert_array_equal(st.field_view("action")[:k].cpu().numpy().ravel(), [r[1] for r in recs_all])
+    np.testing.assert_array_equal(st.field_view("reward")[:k].cpu().numpy().ravel(),
+                                  np.asarray([r[2] for r in recs_all], np.float32))
+    np.testing.assert_array_equal(st.field_view("done")[:k].cpu().numpy().ravel().astype(bool), [r[4] for r in recs_all])
+    np.testing.assert_allclose(st.priorities()[:k].cpu().numpy(),
+                               np.asarray([r[5] for r in recs_all], np.float32), rtol=0)   # stored as given (baseline/PER.py:69-75)
+    # the staging pages are pinned; the NUMA binding is best-effort and must restore the thread's affinity
+    import os
+    before = os.sched_getaffinity(0)
+    t = hostmem.pinned_empty((16,), torch.float32, "cuda:0")
+    assert t.is_pinned() and os.sched_getaffinity(0) == before
