@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="keep the network in NCHW (default: channels_last)")
     ap.add_argument("--unfused-conv1", action="store_true", help="stage the batch and let cuDNN run conv_1")
     ap.add_argument("--cudnn-conv1-wgrad", action="store_true", help="conv_1 weight gradient through a staged fp32 copy + cuDNN instead of csrc/conv1_wgrad.cu")
+    ap.add_argument("--serial-forwards", action="store_true", help="the three forward passes of a step on one stream")
+    ap.add_argument("--unfused-tail", action="store_true", help="dueling tail as separate PyTorch ops instead of csrc/dueling.cu")
     ap.add_argument("--cublas-dense", action="store_true", help="dense heads as cuBLAS fp32 GEMMs instead of the 3xTF32 tcgen05 kernel (csrc/gemm.cu)")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.RMSprop instead of the fused kernel")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="leave cuDNN's algorithm choice to its heuristics")
@@ -226,7 +228,7 @@ def main():
     N, B = 1 << args.log2n, args.batch
     cfg = ApexConfig(BATCHSIZE=B, REPLAY_MEMORY_LEN=N, BUFFER_SIZE=0, LEARNER_DEVICE=str(dev),
                      CHANNELS_LAST=not args.nchw, FUSED_CONV1=not args.unfused_conv1,
-                     FUSED_OPTIM=not args.torch_optim, DENSE_3XTF32=not args.cublas_dense)
+                     FUSED_OPTIM=not args.torch_optim, DENSE_3XTF32=not args.cublas_dense, FUSED_DUELING_TAIL=not args.unfused_tail, PARALLEL_FORWARDS=not args.serial_forwards)
     torch.manual_seed(0)
     learner = Learner(cfg, connect=None, start_replay=False)
     if world > 1:   # identical initial weights on every rank
@@ -381,15 +383,21 @@ def main():
     # Warm-up: the PCIe link reaches its full rate only after ~0.2 s of sustained traffic (tools/h2d_probe.py:
     # 25 -> 47 -> 55 GB/s over the first three 150-copy bursts), and it idles during the device-resident
     # region above, so the steady-state loop is entered with enough untimed steps to move ~5 GB first.
-    for _ in range(max(3, args.warmup) + 170):
-        e2e_step()
-    barrier()
-    k2 = max(10, args.steps // 2)
-    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for _ in range(k2):
-        e2e_step()
-    s1.record()
+    # The host thread that drives the loop is bound to the GPU's NUMA node (numactl --cpunodebind in a
+    # deployment): every step makes ~10 driver calls whose doorbell writes cross the socket interconnect otherwise.
+    from distributed_rl_b200.hostmem import on_gpu_node
+    with on_gpu_node(dev) as bound:
+        for _ in range(max(3, args.warmup) + 170):
+            e2e_step()
+        barrier()
+        k2 = max(10, args.steps // 2)
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        th0 = time.perf_counter()
+        for _ in range(k2):
+            e2e_step()
+        host_ms = (time.perf_counter() - th0) * 1e3
+        s1.record()
     d2h_done[0].synchronize(); d2h_done[1].synchronize()   # the last step's result has been read too
     barrier()
     ms2 = s0.elapsed_time(s1)
@@ -399,7 +407,8 @@ def main():
         ms2 = float(t.item())
     e2e = {"value": B * world * k2 / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 12, "steps": k2,
-           "h2d_GBs": h2d * k2 / (ms2 / 1e3) / 1e9,
+           "h2d_GBs": h2d * k2 / (ms2 / 1e3) / 1e9, "host_ms_per_step": host_ms / k2,
+           "host_thread_bound_to_gpu_numa_node": bool(bound),
            "what": "Replay.commit_ingest + begin_ingest (512 new transitions from pinned host, H2D on the ingest "
                    "stream overlapping the step) + Learner.fused_step() + per-step D2H of the step's scalars to pinned "
                    "host memory (consumed by the host one step later)"}
@@ -420,7 +429,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "clocks": clock_info,
-                "cuda_graph": use_graph, "fused_gather_conv1": bool(cfg.FUSED_CONV1), "fused_optimizer": bool(cfg.FUSED_OPTIM), "tf32_matmul": bool(args.tf32_matmul), "dense_3xtf32": bool(cfg.DENSE_3XTF32), "fused_conv1_wgrad": not args.cudnn_conv1_wgrad, "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
+                "cuda_graph": use_graph, "fused_gather_conv1": bool(cfg.FUSED_CONV1), "fused_optimizer": bool(cfg.FUSED_OPTIM), "tf32_matmul": bool(args.tf32_matmul), "dense_3xtf32": bool(cfg.DENSE_3XTF32), "fused_conv1_wgrad": not args.cudnn_conv1_wgrad, "fused_dueling_tail": bool(cfg.FUSED_DUELING_TAIL), "parallel_forwards": bool(cfg.PARALLEL_FORWARDS), "last_step": {"loss": scal[0], "mean_target": scal[1], "mean_weight": scal[2]}}
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:

@@ -55,6 +55,8 @@ SIGNATURES = {
     "b2rl_gemm_split_pack_into": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "b2rl_gemm_workspace_floats": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "b2rl_gemm_tf32x3": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "b2rl_dueling_forward": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "b2rl_dueling_backward": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2rl_launch_count": (c_i64, []),
 }
 

@@ -201,6 +201,43 @@ class GraphAgent(nn.Module):
                 if isinstance(first, nn.Linear) and first.bias is None:
                     groups.setdefault((self._prev[name][0], first.in_features), []).append(name)
         self._head_groups = {n: tuple(g) for g in groups.values() if len(g) > 1 for n in g}
+        # Dueling tail: two 2-layer heads (relu, linear) combined by Add / Mean / Substract nodes
+        # (cfg/ape_x.json:52-88) -> one kernel after the shared first layer (csrc/dueling.cu).
+        self.fused_dueling_tail = False
+        self._dueling = {}
+        for g in set(self._head_groups.values()):
+            d = self._match_dueling(g)
+            if d is not None:
+                self._dueling[g] = d
+
+    def _match_dueling(self, group):
+        if len(group) != 2:
+            return None
+        cfg = self.cfg
+
+        def two_layer(name):
+            layers = list(getattr(self, name).children())
+            return (len(layers) == 3 and isinstance(layers[0], nn.Linear) and isinstance(layers[1], nn.ReLU)
+                    and isinstance(layers[2], nn.Linear) and layers[0].bias is None and layers[2].bias is None)
+
+        if not all(two_layer(n) for n in group):
+            return None
+        users = {n: [m for m in self._order if n in self._prev[m]] for n in self._order}
+        for adv, val in (group, group[::-1]):
+            if getattr(self, val).MLP_2.out_features != 1 or \
+                    getattr(self, adv).MLP_1.out_features != getattr(self, val).MLP_1.out_features:
+                continue
+            mean = [m for m in users[adv] if cfg[m]["netCat"] == "Mean" and self._prev[m] == [adv]]
+            add = [m for m in users[adv] if cfg[m]["netCat"] == "Add" and sorted(self._prev[m]) == sorted([adv, val])]
+            if len(mean) != 1 or len(add) != 1:
+                continue
+            sub = [m for m in users[add[0]] if cfg[m]["netCat"] == "Substract" and self._prev[m] == [add[0], mean[0]]]
+            inner = (adv, val, add[0], mean[0])
+            if len(sub) != 1 or sorted(users[adv]) != sorted([mean[0], add[0]]) or users[val] != [add[0]] \
+                    or users[add[0]] != sub or users[mean[0]] != sub or any(n in self._outputs for n in inner):
+                continue
+            return {"adv": adv, "val": val, "inner": inner, "out": sub[0]}
+        return None
 
     # -- execution: external inputs first, then upstream outputs (reference order) --
     def forward(self, inputs, preset: dict | None = None):
@@ -212,6 +249,25 @@ class GraphAgent(nn.Module):
                 continue
             group = self._head_groups.get(name) if self.fuse_sibling_heads else None
             if group is not None:
+                duel = self._dueling.get(group) if self.fused_dueling_tail else None
+                if duel is not None and name not in first_out:
+                    from .linear import dueling_tail, dueling_tail_supported, linear3x
+                    x = vals[self._prev[name][0]]
+                    adv, val = getattr(self, duel["adv"]), getattr(self, duel["val"])
+                    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32:
+                        ws = [adv.MLP_1.weight, val.MLP_1.weight]
+                        if self.dense_3xtf32:
+                            cache = None if self._pack_cache is None else self._pack_cache.setdefault(group, {})
+                            h = linear3x(x, ws, cache)
+                        else:
+                            h = torch.nn.functional.linear(x, torch.cat(ws, 0))
+                        if dueling_tail_supported(h, adv.MLP_2.weight, val.MLP_2.weight):
+                            vals[duel["out"]] = dueling_tail(h, adv.MLP_2.weight, val.MLP_2.weight)
+                            for n in duel["inner"]:
+                                vals[n] = None
+                            continue
+                        for n, part in zip((duel["adv"], duel["val"]), torch.split(h, [w.shape[0] for w in ws], dim=-1)):
+                            first_out[n] = part
                 if name not in first_out:
                     x = vals[self._prev[name][0]]
                     ws = [next(iter(getattr(self, n).children())).weight for n in group]
@@ -238,6 +294,19 @@ class GraphAgent(nn.Module):
             yield
         finally:
             self._pack_cache = None
+
+    def prepack_heads(self):
+        """Fill the packed-operand cache (inside packed_heads_cache()) without running a forward pass, so
+        that passes issued on several streams afterwards only read it."""
+        if self._pack_cache is None or not (self.dense_3xtf32 and self.fuse_sibling_heads):
+            return
+        from .linear import _pack_pieces
+        for group in set(self._head_groups.values()):
+            duel = self._dueling.get(group) if self.fused_dueling_tail else None
+            names = (duel["adv"], duel["val"]) if duel is not None else group
+            ws = [next(iter(getattr(self, n).children())).weight for n in names]
+            if ws[0].is_cuda and not any(w.shape[0] % 32 for w in ws[:-1]):
+                self._pack_cache.setdefault(group, {})["fwd"] = _pack_pieces([w.detach() for w in ws], False, True)
 
     def first_conv_node(self):
         """Name of the CNN2D node fed by external input 0, if it starts with the Atari conv_1."""

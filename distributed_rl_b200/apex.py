@@ -53,6 +53,8 @@ class ApexConfig:
     FUSED_CONV1: bool = True        # gather + conv_1 on the tcgen05 tensor cores (csrc/conv1.cu) in fused_step
     FUSED_OPTIM: bool = True        # RMSprop + zero_grad + grad-norm in one launch (csrc/optim.cu)
     CUDNN_BENCHMARK: bool = True    # let cuDNN time its conv_2/conv_3 algorithms once (no precision change)
+    PARALLEL_FORWARDS: bool = True   # the three forward passes of a step on three streams (fork/join inside the graph)
+    FUSED_DUELING_TAIL: bool = True  # heads' second layers + dueling combine in one kernel (csrc/dueling.cu)
     DENSE_3XTF32: bool = True       # dense heads as 3xTF32 tcgen05 GEMMs at fp32 accuracy (csrc/gemm.cu)
 
     @staticmethod
@@ -320,6 +322,7 @@ class Learner:
             self.model.to(memory_format=torch.channels_last)
             self.target_model.to(memory_format=torch.channels_last)
         self.model.dense_3xtf32 = self.target_model.dense_3xtf32 = bool(self.cfg.DENSE_3XTF32)
+        self.model.fused_dueling_tail = self.target_model.fused_dueling_tail = bool(self.cfg.FUSED_DUELING_TAIL)
 
     def build_optim(self):
         info = self.cfg.OPTIM_INFO
@@ -402,12 +405,38 @@ class Learner:
         self._pack2.pack(0, w_on)
         self._pack2.pack(1, w_tg)
         with self.model.packed_heads_cache():     # the online weights are packed once for both passes
-            with torch.no_grad():
-                y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
-                qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
-                qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
-            y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
-            q = self.model.forward_from_conv1(y, False)[0]                       # :78
+            if self.cfg.PARALLEL_FORWARDS:
+                # The three passes are independent until the target kernel: fork them onto three streams
+                # (captured as parallel branches of the step's CUDA graph) so their small kernels overlap.
+                if not hasattr(self, "_fork"):
+                    self._fork = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device),
+                                  torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event())
+                s1, s2, e0, e1, e2 = self._fork
+                cur = torch.cuda.current_stream(self.device)
+                self.model.prepack_heads()
+                with torch.no_grad():
+                    y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
+                e0.record(cur)
+                s1.wait_event(e0)
+                s2.wait_event(e0)
+                with torch.no_grad():
+                    with torch.cuda.stream(s1):
+                        qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
+                        e1.record(s1)
+                    with torch.cuda.stream(s2):
+                        qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
+                        e2.record(s2)
+                y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
+                q = self.model.forward_from_conv1(y, False)[0]                       # :78
+                cur.wait_event(e1)
+                cur.wait_event(e2)
+            else:
+                with torch.no_grad():
+                    y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
+                    qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
+                    qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
+                y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
+                q = self.model.forward_from_conv1(y, False)[0]                       # :78
         notdone = 1.0 - done.to(torch.float32)
         out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
                             self.gamma_n, self.cfg.ALPHA)

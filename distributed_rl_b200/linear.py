@@ -107,3 +107,46 @@ def linear3x(x: torch.Tensor, w, cache: dict | None = None) -> torch.Tensor:
     if len(ws) > 1 and any(m.shape[0] % 32 for m in ws[:-1]):
         ws = [torch.cat(ws, 0)]
     return _Linear3x.apply(x, cache, *ws)
+
+
+class _DuelingTail(torch.autograd.Function):
+    """Q = relu(h[:, :H]) @ Wa.T + relu(h[:, H:]) @ Wv.T - mean_j(adv_j)  in one kernel (csrc/dueling.cu)."""
+
+    @staticmethod
+    def forward(ctx, h, wa, wv):
+        M, H2 = h.shape
+        A, H = wa.shape
+        q = torch.empty(M, A, dtype=torch.float32, device=h.device)
+        _lib.check(_lib.load().b2rl_dueling_forward(h.data_ptr(), M, H, wa.data_ptr(), A, wv.data_ptr(), q.data_ptr(),
+                                                    _stream()))
+        ctx.save_for_backward(h, wa, wv)
+        return q
+
+    @staticmethod
+    def backward(ctx, gq):
+        h, wa, wv = ctx.saved_tensors
+        M, H2 = h.shape
+        A, H = wa.shape
+        gq = gq.contiguous()
+        gh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gwa = torch.empty_like(wa) if need_w else None
+        gwv = torch.empty_like(wv) if need_w else None
+        row_ws = torch.empty(M * (A + 1), dtype=torch.float32, device=h.device)
+        _lib.check(_lib.load().b2rl_dueling_backward(
+            h.data_ptr(), gq.data_ptr(), M, H, wa.data_ptr(), A, wv.data_ptr(),
+            gh.data_ptr() if gh is not None else None, gwa.data_ptr() if need_w else None,
+            gwv.data_ptr() if need_w else None, row_ws.data_ptr(), _stream()))
+        return gh, gwa, gwv
+
+
+def dueling_tail_supported(h: torch.Tensor, wa: torch.Tensor, wv: torch.Tensor) -> bool:
+    return (h.is_cuda and h.dim() == 2 and h.dtype == torch.float32 and h.is_contiguous()
+            and wa.dim() == 2 and wv.shape == (1, wa.shape[1]) and h.shape[1] == 2 * wa.shape[1]
+            and wa.shape[1] % 32 == 0 and wa.shape[1] <= 1024 and wa.shape[0] <= 32
+            and wa.is_contiguous() and wv.is_contiguous())
+
+
+def dueling_tail(h: torch.Tensor, wa: torch.Tensor, wv: torch.Tensor) -> torch.Tensor:
+    """h: [M][2H] pre-activations of the two heads' first layers (advantage | value); wa: [A][H]; wv: [1][H]."""
+    return _DuelingTail.apply(h, wa, wv)

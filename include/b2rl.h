@@ -261,6 +261,18 @@ int64_t b2rl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int64_t ldc)
 int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed_dev, float* c_dev, int64_t M,
                      int64_t N, int64_t K, int64_t ldc, float* workspace_dev, void* stream);
 
+/* Tail of the dueling Q-network after the first dense layer of the two heads (cfg/ape_x.json:52-88: MLP
+ * heads 3136-512-A and 3136-512-1, then the Add / Mean / Substract nodes executed by
+ * baseline/baseAgent.py:287-309):  r = relu(h);  Q_j = r[:H].Wa[j] + r[H:].Wv - mean_i(r[:H].Wa[i]).
+ * h_dev: [M][2H] pre-activations (advantage | value), wa_dev: [A][H], wv_dev: [H], q_dev: [M][A].
+ * backward: gh_dev [M][2H] (may be NULL), gwa_dev [A][H] and gwv_dev [H] (both or neither), row_ws_dev:
+ * M*(A+1) floats of scratch; sums over the batch run in a fixed order.  H % 32 == 0, H <= 1024, A <= 32. */
+int b2rl_dueling_forward(const float* h_dev, int64_t M, int64_t H, const float* wa_dev, int64_t A,
+                         const float* wv_dev, float* q_dev, void* stream);
+int b2rl_dueling_backward(const float* h_dev, const float* gq_dev, int64_t M, int64_t H, const float* wa_dev,
+                          int64_t A, const float* wv_dev, float* gh_dev, float* gwa_dev, float* gwv_dev,
+                          float* row_ws_dev, void* stream);
+
 /* Number of kernels this library has launched in this process (bench.py's
  * `gpu_launches`). */
 int64_t b2rl_launch_count(void);

@@ -101,3 +101,47 @@ def test_stacked_weights_and_cache(L):
     # a non-32-multiple inner piece falls back to one concatenated operand
     y3 = L.linear3x(x.detach(), [w2.detach(), w1.detach()])
     assert _rel(y3, x.detach().double() @ torch.cat([w2, w1]).detach().double().T) < 5e-6
+
+
+@pytest.mark.parametrize("M,H,A", [(512, 512, 6), (1, 32, 1), (37, 96, 18), (64, 1024, 32)])
+def test_dueling_tail_matches_pytorch(L, M, H, A):
+    """csrc/dueling.cu against the unfused node sequence (ReLU, two Linear, Add, Mean, Substract) in fp64."""
+    g = torch.Generator(device="cuda").manual_seed(M + H + A)
+    h = torch.randn(M, 2 * H, device="cuda", generator=g).requires_grad_()
+    wa = (torch.randn(A, H, device="cuda", generator=g) * 0.05).requires_grad_()
+    wv = (torch.randn(1, H, device="cuda", generator=g) * 0.05).requires_grad_()
+    gq = torch.randn(M, A, device="cuda", generator=g)
+    assert L.dueling_tail_supported(h, wa, wv)
+    q = L.dueling_tail(h, wa, wv)
+    q.backward(gq)
+    hd, wad, wvd = (t.detach().double().requires_grad_() for t in (h, wa, wv))
+    r = torch.relu(hd)
+    adv, val = r[:, :H] @ wad.T, r[:, H:] @ wvd.T
+    qr = (adv + val) - adv.mean(dim=-1, keepdim=True)
+    qr.backward(gq.double())
+    for got, ref in ((q, qr.detach()), (h.grad, hd.grad), (wa.grad, wad.grad), (wv.grad, wvd.grad)):
+        assert (got.double() - ref).abs().max().item() <= 2e-6 * max(ref.abs().max().item(), 1e-3)
+    # deterministic
+    h2 = h.detach().clone().requires_grad_()
+    L.dueling_tail(h2, wa, wv).backward(gq)
+    assert torch.equal(h2.grad, h.grad)
+
+
+def test_graph_agent_fused_tail_equals_node_sequence():
+    """GraphAgent with the fused first layer (3xTF32) + fused dueling tail == the plain node-by-node graph."""
+    from distributed_rl_b200.agent import GraphAgent
+    from distributed_rl_b200.apex import default_apex_model
+    torch.manual_seed(0)
+    m = GraphAgent(default_apex_model()).cuda()
+    x = torch.rand(48, 4, 84, 84, device="cuda")
+    outs, grads = [], []
+    for fused in (False, True):
+        m.fused_dueling_tail = m.dense_3xtf32 = fused
+        m.zero_grad(set_to_none=True)
+        q = m([x])[0]
+        q.square().sum().backward()
+        outs.append(q.detach().clone())
+        grads.append([p.grad.clone() for p in m.parameters()])
+    torch.testing.assert_close(outs[1], outs[0], rtol=1e-4, atol=1e-5)
+    for a, b in zip(grads[1], grads[0]):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=1e-4 * b.abs().max().item())
