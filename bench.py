@@ -330,13 +330,48 @@ def main():
                     "note": "algorithmic bytes = sampled frames read (SURVEY §8d: 28 224 B per frame stack) + the two "
                             "fp32 NHWC activation maps written; currently epilogue/issue-bound, not HBM-bound "
                             "(tensor pipe 21.6 % active, profiles/r01_conv1.md)"}
+    if cfg.FUSED_CONV1 and learner._conv1_ready():
+        # fused gather + conv_1 weight gradient: reads B frame stacks + dL/dy (B x 400 x 32 fp32), writes 8192 floats
+        alg_w = B * (28224 + 400 * 32 * 4)
+        gyw = torch.randn(B, 32, 20, 20, device=dev).contiguous(memory_format=torch.channels_last)
+        sf = store.field_view("state")
+        w_us = time_graph(lambda ix: R.conv1_wgrad(sf, ix, gyw))
+        w_ach = alg_w / (w_us * 1e-6) / 1e9
+        kernels["k_conv1_wgrad"] = {"launch_us": w_us, "algorithmic_bytes_per_launch": alg_w, "achieved_GBs": w_ach,
+                                    "frac": w_ach / peak, "int8_TOPS": 2.0 * (B * 400) * 256 * 128 / (w_us * 1e-6) / 1e12,
+                                    "note": "launch_us covers k_conv1_wgrad + k_conv1_wgrad_reduce; reads each sampled s "
+                                            "and its dL/dy once (dL/dy twice: scale pre-scan), no fp32 staging of the frames"}
+    if cfg.DENSE_3XTF32:
+        # the dominant kernel by device time: the 3xTF32 GEMM of the fused 3136 -> 2x512 heads (forward shape)
+        from distributed_rl_b200 import linear as LIN
+        Mg, Ng, Kg = B, 1024, 3136
+        xa = LIN.split_pack(torch.randn(Mg, Kg, device=dev), False, False)
+        wb = LIN.split_pack(torch.randn(Ng, Kg, device=dev) * 0.02, False, True)
+        og = torch.empty(Mg, Ng, device=dev)
+        g_us = time_graph(lambda ix: LIN.gemm_packed(xa, wb, Mg, Ng, Kg, out=og))
+        tpeak = float(peaks.get("bf16_tflops", 1719.3))
+        alg_fl = 2.0 * Mg * Ng * Kg
+        t_ach = alg_fl / (g_us * 1e-6) / 1e12
+        kernels["k_gemm_tf32x3"] = {"launch_us": g_us, "algorithmic_flops_per_launch": alg_fl, "achieved_TFLOPs": t_ach,
+                                    "frac": t_ach / tpeak, "tf32_TFLOPs_executed": 3 * t_ach,
+                                    "frac_of_tf32_peak_est": 3 * t_ach / (tpeak / 2),
+                                    "note": "launch_us covers k_gemm_tf32x3 + k_splitk_reduce for x[512x3136] @ W[1024x3136]^T; "
+                                            "algorithmic flops = the fp32 GEMM (2MNK); the kernel executes 3 TF32 products per "
+                                            "term pair, and TF32 dense peak is half the measured bf16 peak"}
+        roofline = {"kernel": "k_gemm_tf32x3 — fp32-accurate dense heads as 3xTF32 tcgen05 GEMM (largest share of the step)",
+                    "bound": "tensor", "achieved": t_ach, "peak": tpeak, "unit": "TFLOP/s", "frac": t_ach / tpeak,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1719.3",
+                    "traffic": None, "launch_us": g_us, "algorithmic_flops_per_launch": alg_fl,
+                    "note": "achieved counts the fp32 GEMM's 2MNK flops once; the tensor pipe executes 3x that in TF32 "
+                            "(tf32_TFLOPs_executed), whose dense peak is bf16/2 — see kernels[k_gemm_tf32x3]"}
     roofline["kernels"] = kernels
     prof = os.path.join(REPO, "profiles", "r01_traffic.json")
     if os.path.isfile(prof):
         try:
             tr = json.load(open(prof))
-            key = "k_conv1_fused<2>" if "k_conv1_fused<2>" in kernels else "k_gather_bulk"
-            roofline["traffic"] = tr.get(key)
+            key = next((k for k in ("k_gemm_tf32x3", "k_conv1_fused<2>", "k_gather_bulk") if k in kernels and k in tr),
+                       None)
+            roofline["traffic"] = tr.get(key) if key else None
         except Exception:
             pass
 

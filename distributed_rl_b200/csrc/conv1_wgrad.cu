@@ -10,12 +10,12 @@
 //
 // Arithmetic: the GEMM is D[e = (c,ky,kx)][co] = sum_p A[e][p] * G[co][p] with p = (k, oy, ox).
 // A holds exact uint8 pixels, so the MMA runs in kind::i8.  The fp32 output gradient is written as
-// four signed 7-bit digits against a per-(CTA, channel) power-of-two scale,
-//     gy = s * (q0 + q1/2^7 + q2/2^14 + q3/2^21)     (exact for |gy| >= s*2^-3, else +- s*2^-22),
+// four balanced base-256 digits (int8) against a per-(CTA, channel) power-of-two scale s > max|gy| / 127,
+//     gy = s * (q0 + q1/2^8 + q2/2^16 + q3/2^24)     (exact for |gy| >= s, else rounded at s * 2^-24),
 // the digits being four groups of C_OUT rows of the B operand (N = 4*C_OUT).  Integer accumulation over
-// all of the CTA's frame stacks is exact; the epilogue recombines the digit sums in int64 and scales
-// once, so every CTA partial is the exact sum of pixel x (28-bit fixed-point gy).  Partials of the
-// CTAs are summed in fp64 by k_conv1_wgrad_reduce (deterministic, no atomics).
+// all of the CTA's frame stacks is exact; the epilogue recombines the digit sums pairwise in int64 with
+// one fp32 rounding per pair, so every CTA partial is the sum of pixel x (32-bit fixed-point gy) to
+// ~1 ulp.  Partials of the CTAs are summed in fp64 by k_conv1_wgrad_reduce (deterministic, no atomics).
 //
 // Warp roles per CTA (persistent, one CTA per SM, 20 warps):
 //   warp 0        TMA loader: one 28 224-byte frame stack per item
@@ -26,6 +26,8 @@
 //                 (warp = 8 channels x half of a chunk's 16-position units)
 //   warps 16-19   then run the epilogue once: TMEM -> int64 recombination -> partial[cta][co][e]
 #include "common.cuh"
+
+#include <stdlib.h>
 
 namespace b2rl {
 namespace conv1w {
@@ -42,7 +44,7 @@ constexpr int A_BYTES = E_TOTAL * KCHUNK;          // 32 KiB
 constexpr int STAGES = 3;
 constexpr int THREADS = 640;
 constexpr int A_PRODUCERS = 256, B_PRODUCERS = 256;
-constexpr int MAX_ITEMS_PER_CTA = 160;             // int32 accumulators: 127*255*400*T < 2^31
+constexpr int MAX_ITEMS_PER_CTA = 160;             // int32 accumulators: 128*255*400*T < 2^31
 
 __device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) {
@@ -106,6 +108,7 @@ struct Params {
   int64_t n, capacity;
   const float* gy;           // [n][400][C_OUT] fp32 (NHWC)
   float* partial;            // [gridDim.x][C_OUT][256]
+  long long* dbg;            // optional [16] cycle counters of CTA 0 (B2RL_CONV1_DBG=1), else nullptr
 };
 
 template <int C_OUT>
@@ -165,7 +168,9 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
       for (int64_t k = first; k < P.n; k += stride) {
         for (int j = 0; j < CHUNKS; ++j, ++at) {
           const int stage = at % STAGES;
+          const long long c0 = clock64();
           mbar_wait(&s_full[stage], (at / STAGES) & 1);
+          const long long c1 = clock64();
           tc_fence_after();
           const uint32_t a_base = sptr(sStage + stage * STAGE_BYTES), b_base = a_base + A_BYTES;
           const int ksteps = (j < CHUNKS - 1) ? 4 : 1;   // last chunk: positions 384..399 (+16 zeros)
@@ -176,35 +181,53 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
             started = 1u;
           }
           tc_commit(&s_empty[stage]);
+          if (P.dbg && blockIdx.x == 0) { P.dbg[0] += c1 - c0; P.dbg[1] += clock64() - c1; }
         }
       }
       tc_commit(&acc_full);
     }
   } else if (warp >= 4) {
     // -------- all producers first find max |gy| per channel over this CTA's items (the digit scale) --------
-    {
-      const int pt = threadIdx.x - 128;                 // 0..511
-      const int co = pt % C_OUT;
-      uint32_t m = 0u;
+    const long long t_start = clock64();
+    if (warp >= 12) {
+      // -------- the B producers first find max |gy| per channel over this CTA's items (the digit scale);
+      //          the A producers need no scale and start filling the pipeline meanwhile --------
+      const int pt = threadIdx.x - 384;                 // 0..255
+      const int c4 = (pt * 4) % C_OUT;                  // this thread always sees channels c4..c4+3 (1024 % C_OUT == 0)
+      uint4 m = make_uint4(0u, 0u, 0u, 0u);
       for (int64_t k = first; k < P.n; k += stride) {
-        const float* g = P.gy + k * (int64_t)(POS * C_OUT);
-#pragma unroll 5
-        for (int e = pt; e < POS * C_OUT; e += 512) m = max(m, __float_as_uint(g[e]) & 0x7FFFFFFFu);   // 512 % C_OUT == 0
+        const uint4* g = reinterpret_cast<const uint4*>(P.gy + k * (int64_t)(POS * C_OUT));
+#pragma unroll
+        for (int i = 0; i < (POS * C_OUT / 4 + 255) / 256; ++i) {
+          const int e = pt + 256 * i;
+          if (e < POS * C_OUT / 4) {
+            const uint4 v = g[e];
+            m.x = max(m.x, v.x & 0x7FFFFFFFu); m.y = max(m.y, v.y & 0x7FFFFFFFu);
+            m.z = max(m.z, v.z & 0x7FFFFFFFu); m.w = max(m.w, v.w & 0x7FFFFFFFu);
+          }
+        }
       }
-      atomicMax(&s_absmax[co], m);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      atomicMax(&s_absmax[c4 + 0], m.x); atomicMax(&s_absmax[c4 + 1], m.y);
+      atomicMax(&s_absmax[c4 + 2], m.z); atomicMax(&s_absmax[c4 + 3], m.w);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    const bool probe = P.dbg && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 12);
+    if (probe) P.dbg[warp == 4 ? 2 : 6] += clock64() - t_start;
     if (warp < 12) {
       // ------------------- A producers: transposed im2col, uint8 -------------------
       const int aw = warp - 4;
       int at = 0, it = 0;
       for (int64_t k = first; k < P.n; k += stride, ++it) {
         const int s = it & 1;
+        long long a0 = clock64();
         mbar_wait(&raw_full[s], (it >> 1) & 1);
+        if (probe) P.dbg[3] += clock64() - a0;
         const uint8_t* raw = sRaw + s * RAW_STRIDE;
         for (int j = 0; j < CHUNKS; ++j, ++at) {
           const int stage = at % STAGES;
+          a0 = clock64();
           mbar_wait(&s_empty[stage], ((at / STAGES) & 1) ^ 1);
+          const long long a1 = clock64();
           const int p0 = j * KCHUNK + 4 * lane;          // this lane's 4 consecutive positions (same oy: 20 % 4 == 0)
           if (p0 < POS) {
             const int oy = p0 / OHW, ox0 = p0 - oy * OHW;
@@ -212,24 +235,32 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
             uint8_t* dstA = sStage + stage * STAGE_BYTES;
             const int unit = lane >> 2, word = (lane & 3) * 4;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const int eq = aw * 8 + r;                 // (c, ky, kx half): 64 quads of 4 patch elements
-              const int c = eq >> 4, ky = (eq >> 1) & 7, kxh = eq & 1;
-              const uint32_t* src = reinterpret_cast<const uint32_t*>(src0 + c * (HW * HW) + ky * HW + 4 * kxh);
-              const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];   // pixels of positions p0..p0+3
-              const int e0 = c * 64 + ky * 8 + 4 * kxh;
+            for (int r = 0; r < 4; ++r) {
+              const int cy = aw * 4 + r;                 // (c, ky): 32 rows of 8 patch elements (kx = 0..7)
+              const int c = cy >> 3, ky = cy & 7;
+              const uint32_t* src = reinterpret_cast<const uint32_t*>(src0 + c * (HW * HW) + ky * HW);
+              // pixels 4*ox0 .. 4*ox0+19: word i holds kx = 0..3 of position p0+i, word i+1 its kx = 4..7
+              const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3], w4 = src[4];
+              const int e0 = c * 64 + ky * 8;
+              // 4x4 byte transposes: out[kx] = {w_a.b[kx], w_b.b[kx], w_c.b[kx], w_d.b[kx]} = positions p0..p0+3 of element kx
+              const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w0, w1, 0x7362);
+              const uint32_t t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
+              const uint32_t u0 = __byte_perm(w1, w2, 0x5140), u1 = __byte_perm(w1, w2, 0x7362);
+              const uint32_t u2 = __byte_perm(w3, w4, 0x5140), u3 = __byte_perm(w3, w4, 0x7362);
+              const uint32_t o[8] = {__byte_perm(t0, t2, 0x5410), __byte_perm(t0, t2, 0x7632),
+                                     __byte_perm(t1, t3, 0x5410), __byte_perm(t1, t3, 0x7632),
+                                     __byte_perm(u0, u2, 0x5410), __byte_perm(u0, u2, 0x7632),
+                                     __byte_perm(u1, u3, 0x5410), __byte_perm(u1, u3, 0x7632)};
 #pragma unroll
-              for (int kx = 0; kx < 4; ++kx) {
-                const uint32_t sel = (uint32_t)(kx | ((4 + kx) << 4));
-                const uint32_t t01 = __byte_perm(w0, w1, sel), t23 = __byte_perm(w2, w3, sel);
-                const int e = e0 + kx;
-                *reinterpret_cast<uint32_t*>(dstA + sw_row(e) + ((unit ^ (e & 7)) << 4) + word) =
-                    __byte_perm(t01, t23, 0x5410);
+              for (int kx = 0; kx < 8; ++kx) {           // row e0 + kx: (e & 7) == kx
+                *reinterpret_cast<uint32_t*>(dstA + sw_row(e0 + kx) + ((unit ^ kx) << 4) + word) = o[kx];
               }
             }
           }
+          const long long a2 = clock64();
           fence_async_smem();
           mbar_arrive(&s_full[stage]);
+          if (probe) { P.dbg[4] += a1 - a0; P.dbg[5] += a2 - a1; P.dbg[13] += clock64() - a2; }
         }
         mbar_arrive(&raw_empty[s]);
       }
@@ -239,69 +270,82 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
       const int c3 = lane & 7, pq = lane >> 3;
       const int co = 8 * bw + c3;
       const bool active = (8 * bw) < C_OUT;
-      float inv_s = 1.0f;
+      float inv_s24 = 16777216.0f;
       if (active) {
         const float t = __uint_as_float(s_absmax[co]) / 127.0f;
         int e = (int)((__float_as_uint(t) >> 23) & 0xFF) + 1;     // s = 2^(e-127) > t
         e = e < 27 ? 27 : (e > 227 ? 227 : e);
-        inv_s = __uint_as_float((uint32_t)(254 - e) << 23);
+        inv_s24 = __uint_as_float((uint32_t)(254 - e + 24) << 23);   // 2^24 / s
       }
-      int at = 0;
-      for (int64_t k = first; k < P.n; k += stride) {
-        const float* g = P.gy + k * (int64_t)(POS * C_OUT) + co;
-        for (int j = 0; j < CHUNKS; ++j, ++at) {
-          const int stage = at % STAGES;
-          // this warp's units of the chunk: 4 of 8 (last chunk: unit 0 = positions 384..399, unit 1 = zeros)
-          const int u0 = (j < CHUNKS - 1) ? uh * 4 : uh, nu = (j < CHUNKS - 1) ? 4 : 1;
-          float v[4][4];
-          if (active) {                                            // all loads of the chunk in flight before the wait
+      // chunk `at` = (item at/4, chunk at%4); the loads of chunk at+1 are issued before chunk at is converted
+      const int64_t n_items = (P.n - first + stride - 1) / stride;
+      const int total = (int)n_items * CHUNKS;
+      auto load_chunk = [&](int at, float (&v)[4][4]) {
+        const int j = at & 3;
+        const float* g = P.gy + (first + (int64_t)(at >> 2) * stride) * (int64_t)(POS * C_OUT) + co;
+        const int u0 = (j < CHUNKS - 1) ? uh * 4 : uh, nu = (j < CHUNKS - 1) ? 4 : 1;
 #pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-              const int p = j * KCHUNK + (u0 + uu) * 16 + 4 * pq;
+        for (int uu = 0; uu < 4; ++uu) {
+          const int p = j * KCHUNK + (u0 + uu) * 16 + 4 * pq;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) v[uu][i] = (uu < nu && p < POS) ? g[(int64_t)(p + i) * C_OUT] : 0.0f;
-            }
-          }
-          mbar_wait(&s_empty[stage], ((at / STAGES) & 1) ^ 1);
-          if (active) {
-            uint8_t* dstB = sStage + stage * STAGE_BYTES + A_BYTES;
-#pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-              if (uu >= nu) break;
-              uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float x = v[uu][i] * inv_s;                        // exact: power-of-two scale, |x| <= 127
-                int q0 = __float2int_rn(x);
-                q0 = max(-127, min(127, q0));
-                x = (x - (float)q0) * 128.0f;                       // exact
-                const int q1 = __float2int_rn(x);
-                x = (x - (float)q1) * 128.0f;
-                const int q2 = __float2int_rn(x);
-                x = (x - (float)q2) * 128.0f;
-                int q3 = __float2int_rn(x);
-                q3 = max(-127, min(127, q3));
-                d0 |= (uint32_t)(q0 & 0xFF) << (8 * i);
-                d1 |= (uint32_t)(q1 & 0xFF) << (8 * i);
-                d2 |= (uint32_t)(q2 & 0xFF) << (8 * i);
-                d3 |= (uint32_t)(q3 & 0xFF) << (8 * i);
-              }
-              const int off = (((u0 + uu) ^ c3) << 4) + pq * 4;    // rows d*C_OUT + co: (row & 7) == c3
-              *reinterpret_cast<uint32_t*>(dstB + sw_row(0 * C_OUT + co) + off) = d0;
-              *reinterpret_cast<uint32_t*>(dstB + sw_row(1 * C_OUT + co) + off) = d1;
-              *reinterpret_cast<uint32_t*>(dstB + sw_row(2 * C_OUT + co) + off) = d2;
-              *reinterpret_cast<uint32_t*>(dstB + sw_row(3 * C_OUT + co) + off) = d3;
-            }
-          }
-          fence_async_smem();
-          mbar_arrive(&s_full[stage]);
+          for (int i = 0; i < 4; ++i) v[uu][i] = (uu < nu && p < POS) ? g[(int64_t)(p + i) * C_OUT] : 0.0f;
         }
+      };
+      float v[4][4], vn[4][4];
+      if (active && total > 0) load_chunk(0, v);
+      for (int at = 0; at < total; ++at) {
+        const int stage = at % STAGES, j = at & 3;
+        // this warp's units of the chunk: 4 of 8 (last chunk: unit 0 = positions 384..399, unit 1 = zeros)
+        const int u0 = (j < CHUNKS - 1) ? uh * 4 : uh, nu = (j < CHUNKS - 1) ? 4 : 1;
+        if (active && at + 1 < total) load_chunk(at + 1, vn);
+        const long long b0 = clock64();
+        mbar_wait(&s_empty[stage], ((at / STAGES) & 1) ^ 1);
+        const long long b1 = clock64();
+        if (active) {
+          uint8_t* dstB = sStage + stage * STAGE_BYTES + A_BYTES;
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu) {
+            if (uu >= nu) break;
+            // X = gy / s * 2^24 as an int32 (exact: power-of-two scale, |X| <= 127 * 2^24); balanced base-256 digits
+            // via the bias 0x00808080: the three low bytes come out as q + 128, the top byte is q0 itself.
+            uint32_t Y[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Y[i] = (uint32_t)__float2int_rn(v[uu][i] * inv_s24) + 0x00808080u;
+            // 4x4 byte transpose: digit d of the four positions packed into one word
+            const uint32_t t0 = __byte_perm(Y[0], Y[1], 0x5140), t1 = __byte_perm(Y[0], Y[1], 0x7362);
+            const uint32_t t2 = __byte_perm(Y[2], Y[3], 0x5140), t3 = __byte_perm(Y[2], Y[3], 0x7362);
+            const uint32_t d3 = __byte_perm(t0, t2, 0x5410) ^ 0x80808080u, d2 = __byte_perm(t0, t2, 0x7632) ^ 0x80808080u;
+            const uint32_t d1 = __byte_perm(t1, t3, 0x5410) ^ 0x80808080u, d0 = __byte_perm(t1, t3, 0x7632);
+            const int off = (((u0 + uu) ^ c3) << 4) + pq * 4;    // rows d*C_OUT + co: (row & 7) == c3
+            *reinterpret_cast<uint32_t*>(dstB + sw_row(0 * C_OUT + co) + off) = d0;
+            *reinterpret_cast<uint32_t*>(dstB + sw_row(1 * C_OUT + co) + off) = d1;
+            *reinterpret_cast<uint32_t*>(dstB + sw_row(2 * C_OUT + co) + off) = d2;
+            *reinterpret_cast<uint32_t*>(dstB + sw_row(3 * C_OUT + co) + off) = d3;
+          }
+        }
+        const long long b2 = clock64();
+        fence_async_smem();
+        mbar_arrive(&s_full[stage]);
+        if (probe) { P.dbg[7] += b1 - b0; P.dbg[8] += b2 - b1; P.dbg[12] += clock64() - b2; }
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[uu][i] = vn[uu][i];
       }
       if (warp >= 16) {
         // ------------------------------- epilogue (once) -------------------------------
         const int wq = warp & 3;
+        const long long e0 = clock64();
         mbar_wait(&acc_full, 0);
+        const long long e1 = clock64();
         tc_fence_after();
+        float my_scale = 0.0f;                               // lane = channel: s * 2^-8 / 255
+        if (lane < C_OUT) {
+          const float t = __uint_as_float(s_absmax[lane]) / 127.0f;
+          int ex = (int)((__float_as_uint(t) >> 23) & 0xFF) + 1;
+          ex = ex < 27 ? 27 : (ex > 227 ? 227 : ex);
+          my_scale = __uint_as_float((uint32_t)(ex - 8) << 23) / 255.0f;
+        }
         float* out = P.partial + (int64_t)blockIdx.x * (C_OUT * E_TOTAL);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -318,15 +362,14 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int cc = cg * 16 + i;
-              const float t = __uint_as_float(s_absmax[cc]) / 127.0f;
-              int ex = (int)((__float_as_uint(t) >> 23) & 0xFF) + 1;
-              ex = ex < 27 ? 27 : (ex > 227 ? 227 : ex);
-              const double s = (double)__uint_as_float((uint32_t)ex << 23);
-              const long long V = ((long long)q0[i] << 21) + ((long long)q1[i] << 14) + ((long long)q2[i] << 7) + (long long)q3[i];
-              out[cc * E_TOTAL + e] = (float)((double)V * (s * (1.0 / 2097152.0) / 255.0));
+              // digit sums recombined pairwise in exact int64, one fp32 rounding per half, one FMA, the scale
+              const float fu = (float)((long long)q0[i] * 256 + (long long)q1[i]);
+              const float ft = (float)((long long)q2[i] * 256 + (long long)q3[i]);
+              out[cc * E_TOTAL + e] = __fmaf_rn(ft, 1.0f / 65536.0f, fu) * __shfl_sync(0xffffffffu, my_scale, cc);
             }
           }
         }
+        if (P.dbg && blockIdx.x == 0 && warp == 16 && lane == 0) { P.dbg[9] += e1 - e0; P.dbg[10] += clock64() - e1; P.dbg[11] += clock64() - t_start; }
       }
     }
   }
@@ -342,8 +385,16 @@ __global__ void __launch_bounds__(256)
 k_conv1_wgrad_reduce(const float* __restrict__ partial, int n_parts, int numel, int accumulate, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= numel) return;
-  double s = 0.0;
-  for (int p = 0; p < n_parts; ++p) s += (double)partial[(int64_t)p * numel + i];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four interleaved chains (fixed order): four loads in flight
+  int p = 0;
+  for (; p + 3 < n_parts; p += 4) {
+    s0 += (double)partial[(int64_t)p * numel + i];
+    s1 += (double)partial[(int64_t)(p + 1) * numel + i];
+    s2 += (double)partial[(int64_t)(p + 2) * numel + i];
+    s3 += (double)partial[(int64_t)(p + 3) * numel + i];
+  }
+  for (; p < n_parts; ++p) s0 += (double)partial[(int64_t)p * numel + i];
+  const double s = (s0 + s1) + (s2 + s3);
   out[i] = accumulate ? (float)((double)out[i] + s) : (float)s;
 }
 
@@ -394,20 +445,31 @@ extern "C" int b2rl_conv1_wgrad(const uint8_t* frames_dev, int64_t capacity, con
   if (!sms[dev & 63]) B2RL_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
   cudaStream_t st = (cudaStream_t)stream;
   const int numel = c_out * conv1w::E_TOTAL;
+  static long long* dbg_buf = nullptr;
+  if (getenv("B2RL_CONV1_DBG") && !dbg_buf) B2RL_CUDA(cudaMalloc(&dbg_buf, 16 * sizeof(long long)));
+  if (dbg_buf) B2RL_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), st));
   const int64_t per_launch = (int64_t)sms[dev & 63] * conv1w::MAX_ITEMS_PER_CTA;   // int32 accumulator bound
   for (int64_t off = 0; off < n; off += per_launch) {
     const int64_t m = (n - off < per_launch) ? n - off : per_launch;
     conv1w::Params P{frames_dev, idx_dev ? idx_dev + off : nullptr, m, capacity,
-                     gy_dev + off * (int64_t)(conv1w::POS * c_out), workspace_dev};
+                     gy_dev + off * (int64_t)(conv1w::POS * c_out), workspace_dev, dbg_buf};
     if (!idx_dev) P.frames = frames_dev + off * conv1w::FRAME_BYTES, P.capacity = capacity - off;
     const unsigned grid = (unsigned)((m < sms[dev & 63]) ? m : sms[dev & 63]);
     B2RL_CUDA(c_out == 32 ? wgrad_launch<32>(P, grid, st) : wgrad_launch<16>(P, grid, st));
     count_launch();
     B2RL_CHECK_LAUNCH();
-    conv1w::k_conv1_wgrad_reduce<<<(numel + 255) / 256, 256, 0, st>>>(workspace_dev, (int)grid, numel,
+    conv1w::k_conv1_wgrad_reduce<<<(numel + 63) / 64, 64, 0, st>>>(workspace_dev, (int)grid, numel,
                                                                        (accumulate || off > 0) ? 1 : 0, gw_dev);
     count_launch();
     B2RL_CHECK_LAUNCH();
+  }
+  if (dbg_buf) {   // profiling aid: per-role cycle counters of CTA 0 (synchronous; never set in production)
+    long long h[16];
+    B2RL_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    static const char* names[14] = {"mma:wait s_full", "mma:issue+commit", "A:prescan", "A:wait raw_full", "A:wait s_empty",
+                                    "A:build", "B:prescan", "B:wait s_empty", "B:build", "epi:wait acc", "epi:work",
+                                    "producers total", "B:fence+arrive", "A:fence+arrive"};
+    for (int i = 0; i < 14; ++i) fprintf(stderr, "[conv1 wgrad dbg] n %lld %-20s %lld\n", (long long)n, names[i], h[i]);
   }
   return B2RL_OK;
 }

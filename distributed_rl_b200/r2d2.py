@@ -60,6 +60,7 @@ class R2D2Config:
     OPTIM_INFO: dict = field(default_factory=lambda: {"name": "adam", "lr": 1e-4, "eps": 0.001})
     MODEL: dict = field(default_factory=default_r2d2_model)
     FUSED_CONV1: bool = True     # conv_1 of every frame through libb2rl's tcgen05 kernel (gather fused)
+    FUSED_HEADS: bool = True     # dueling heads: 3xTF32 tcgen05 GEMM + fused tail kernels (csrc/gemm.cu, csrc/dueling.cu)
 
     @staticmethod
     def from_configuration():
@@ -117,6 +118,8 @@ class Learner:
         self.device = torch.device(self.cfg.LEARNER_DEVICE)
         self.model = GraphAgent(self.cfg.MODEL).to(self.device)
         self.target_model = GraphAgent(self.cfg.MODEL).to(self.device)
+        for m in (self.model, self.target_model):
+            m.dense_3xtf32 = m.fused_dueling_tail = bool(self.cfg.FUSED_HEADS) and self.device.type == "cuda"
         self.optim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
         self.connect = connect
         self.memory = Replay(self.cfg, connect)
