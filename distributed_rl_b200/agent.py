@@ -32,6 +32,38 @@ def _act(name):
     return None if _ACT[name] is None else _ACT[name]()
 
 
+class _ConvSplitBackward(torch.autograd.Function):
+    """conv2d whose backward computes dL/dx on the current stream and hands dL/dW to the active
+    WeightGradSink (linear.py): the weight gradient only feeds the optimizer, so it leaves the critical path."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.sp = (tuple(stride), tuple(padding))
+        return torch.nn.functional.conv2d(x, w, None, stride, padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .linear import WeightGradSink, _SINK  # noqa: F401  (module attribute read at call time below)
+        from . import linear as _lin
+        x, w = ctx.saved_tensors
+        stride, padding = ctx.sp
+        bw = torch.ops.aten.convolution_backward
+
+        def run(mask):
+            return bw(gy, x, w, None, stride, padding, (1, 1), False, (0, 0), 1, mask)
+
+        gx = run((True, False, False))[0] if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            if WeightGradSink.usable((w,)):
+                sink = _lin._SINK
+                sink.submit(lambda: sink.accumulate(w, run((False, True, False))[1]), keep=(gy, x))
+            else:
+                gw = run((False, True, False))[1]
+        return gx, gw, None, None
+
+
 class ConvStack(nn.Sequential):
     """netCat CNN2D: conv layers (bias=False), then Flatten at fSize == -1."""
 
@@ -50,10 +82,18 @@ class ConvStack(nn.Sequential):
             if a is not None:
                 self.add_module(f"act_{i + 1}", a)
 
+    split_backward = False     # route Conv2d layers through _ConvSplitBackward (set by the learner)
+
+    def _run(self, layer, x):
+        if self.split_backward and isinstance(layer, nn.Conv2d) and x.is_cuda and torch.is_grad_enabled() \
+                and layer.bias is None and layer.dilation == (1, 1) and layer.groups == 1:
+            return _ConvSplitBackward.apply(x, layer.weight, layer.stride, layer.padding)
+        return layer(x)
+
     def forward(self, xs):
         x = xs[0] if isinstance(xs, (tuple, list)) else xs
         for layer in self:
-            x = layer(x)
+            x = self._run(layer, x)
         return x
 
     def is_atari_conv1(self) -> bool:
@@ -70,7 +110,7 @@ class ConvStack(nn.Sequential):
         """Continue after conv_1: `y` is conv_1's output (pre- or post-ReLU)."""
         x = y
         for layer in list(self.children())[2 if relu_applied else 1:]:
-            x = layer(x)
+            x = self._run(layer, x)
         return x
 
 

@@ -53,6 +53,7 @@ class ApexConfig:
     FUSED_CONV1: bool = True        # gather + conv_1 on the tcgen05 tensor cores (csrc/conv1.cu) in fused_step
     FUSED_OPTIM: bool = True        # RMSprop + zero_grad + grad-norm in one launch (csrc/optim.cu)
     CUDNN_BENCHMARK: bool = True    # let cuDNN time its conv_2/conv_3 algorithms once (no precision change)
+    DEFERRED_WGRAD: bool = True      # weight gradients on a side stream, off the critical path of backward
     PARALLEL_FORWARDS: bool = True   # the three forward passes of a step on three streams (fork/join inside the graph)
     FUSED_DUELING_TAIL: bool = True  # heads' second layers + dueling combine in one kernel (csrc/dueling.cu)
     DENSE_3XTF32: bool = True       # dense heads as 3xTF32 tcgen05 GEMMs at fp32 accuracy (csrc/gemm.cu)
@@ -440,7 +441,18 @@ class Learner:
         notdone = 1.0 - done.to(torch.float32)
         out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
                             self.gamma_n, self.cfg.ALPHA)
-        q.backward(out["grad_q"])
+        if self.cfg.DEFERRED_WGRAD and self._fused_optim:      # grads are pre-allocated and zeroed by the optimizer
+            if not hasattr(self, "_sink"):
+                from .linear import WeightGradSink
+                self._sink = WeightGradSink(self.device)
+                getattr(self.model, self._conv_name).split_backward = True
+                if self._world > 1:
+                    self._bucket.attach_sink(self._sink)
+            with self._sink.active():
+                q.backward(out["grad_q"])
+            self._sink.join()
+        else:
+            q.backward(out["grad_q"])
         if self._world > 1:
             self._bucket.finish()
         return out

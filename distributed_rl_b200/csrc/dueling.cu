@@ -211,6 +211,9 @@ extern "C" int b2rl_dueling_forward(const float* h_dev, int64_t M, int64_t H, co
   return B2RL_OK;
 }
 
+extern "C" int b2rl_dueling_backward_w(const float* h_dev, const float* row_ws_dev, int64_t M, int64_t H, int64_t A,
+                                       float* gwa_dev, float* gwv_dev, void* stream);
+
 extern "C" int b2rl_dueling_backward(const float* h_dev, const float* gq_dev, int64_t M, int64_t H,
                                      const float* wa_dev, int64_t A, const float* wv_dev, float* gh_dev,
                                      float* gwa_dev, float* gwv_dev, float* row_ws_dev, void* stream) {
@@ -228,7 +231,16 @@ extern "C" int b2rl_dueling_backward(const float* h_dev, const float* gq_dev, in
     count_launch();
     B2RL_CHECK_LAUNCH();
   }
-  if (gwa_dev) {
+  if (gwa_dev) return b2rl_dueling_backward_w(h_dev, row_ws_dev, M, H, A, gwa_dev, gwv_dev, stream);
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_dueling_backward_w(const float* h_dev, const float* row_ws_dev, int64_t M, int64_t H, int64_t A,
+                                       float* gwa_dev, float* gwv_dev, void* stream) {
+  if (int rc = dueling_check(h_dev, M, H, A)) return rc;
+  B2RL_REQUIRE(row_ws_dev && gwa_dev && gwv_dev, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
     const unsigned grid = (unsigned)(2 * H / 8);
     if (A <= 8)
       dueling::k_dueling_backward_w<8><<<grid, 256, 0, st>>>(h_dev, row_ws_dev, (int)M, (int)H, (int)A, gwa_dev, gwv_dev);

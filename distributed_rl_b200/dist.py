@@ -68,8 +68,16 @@ class FlatGradBucket:
                 self._work = self._reduce(self._early, async_op=True)
                 self._early_needs_div = gloo
 
+        self._early_hook, self._early_params = hook, early
         for p in early:
             p.register_post_accumulate_grad_hook(hook)
+
+    def attach_sink(self, sink) -> None:
+        """Weight gradients that bypass autograd's AccumulateGrad (linear.WeightGradSink) report here instead:
+        the early all-reduce is then launched from the sink's side stream as soon as the last early gradient
+        has been accumulated there."""
+        for p in getattr(self, "_early_params", []):
+            sink.on_ready[id(p)] = self._early_hook
 
     def finish(self) -> None:
         """After backward: reduce the late (small) part, then wait for the early part."""

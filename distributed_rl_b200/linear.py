@@ -17,6 +17,72 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class WeightGradSink:
+    """Weight gradients off the critical path of backward.
+
+    dL/dW of a layer feeds only the optimizer, while dL/dx feeds the rest of the backward pass.  Inside
+    `with sink.active():` the layers of this module compute dL/dW on the sink's side stream, accumulate it into
+    the (pre-allocated) `.grad` there and return None for it to autograd; `join()` makes the caller's stream
+    wait for all of it (call it after backward, before the optimizer).  Tensors handed to the side stream are
+    kept alive until the join, so their memory cannot be reused by the main stream while the side stream reads it.
+    `on_ready` callbacks (e.g. the early gradient all-reduce of data parallelism) run on the side stream too."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._fork, self._done = torch.cuda.Event(), torch.cuda.Event()
+        self._keep, self._pending = [], False
+        self.on_ready = {}          # id(param) -> callable, invoked (side stream) after that param's grad is complete
+
+    @staticmethod
+    def usable(params) -> bool:
+        return _SINK is not None and all(p.grad is not None for p in params)
+
+    def submit(self, fn, keep=()):
+        cur = torch.cuda.current_stream(self.device)
+        self._fork.record(cur)
+        self.stream.wait_event(self._fork)
+        with torch.cuda.stream(self.stream):
+            fn()
+        self._keep.extend(keep)
+        self._pending = True
+
+    def accumulate(self, param, grad):
+        """(side stream) param.grad += grad, then the parameter's ready callback."""
+        param.grad.add_(grad.view_as(param.grad) if grad.shape == param.grad.shape else grad)
+        cb = self.on_ready.get(id(param))
+        if cb is not None:
+            cb(param)
+
+    def join(self):
+        if self._pending:
+            self._done.record(self.stream)
+            torch.cuda.current_stream(self.device).wait_event(self._done)
+            self._pending = False
+        self._keep.clear()
+
+    def active(self):
+        return _SinkContext(self)
+
+
+class _SinkContext:
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __enter__(self):
+        global _SINK
+        self._old, _SINK = _SINK, self.sink
+        return self.sink
+
+    def __exit__(self, *exc):
+        global _SINK
+        _SINK = self._old
+        return False
+
+
+_SINK: WeightGradSink | None = None
+
+
 def split_pack(x: torch.Tensor, transpose: bool, b_role: bool) -> torch.Tensor:
     """{hi, lo} TF32 operand image of a 2-D fp32 CUDA matrix (or of its transpose)."""
     if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda:
@@ -94,8 +160,18 @@ class _Linear3x(torch.autograd.Function):
             gx = gemm_packed(split_pack(gy, False, False), _pack_pieces(ws, True, True), M, K, N)
         if any(ctx.needs_input_grad[2:]):
             # dW[N][K] = gy^T[N][M] @ x[M][K]: contraction over M
-            gw = gemm_packed(split_pack(gy, True, False), split_pack(x, True, True), N, K, M)
-            gws = list(torch.split(gw, [w.shape[0] for w in ws], 0))
+            def wgrad():
+                gw = gemm_packed(split_pack(gy, True, False), split_pack(x, True, True), N, K, M)
+                return list(torch.split(gw, [w.shape[0] for w in ws], 0))
+            if WeightGradSink.usable(ws):
+                sink = _SINK
+
+                def deferred():
+                    for w, g in zip(ws, wgrad()):
+                        sink.accumulate(w, g)
+                sink.submit(deferred, keep=(gy, x))
+            else:
+                gws = wgrad()
         return (gx, None, *gws)
 
 
@@ -130,13 +206,26 @@ class _DuelingTail(torch.autograd.Function):
         gq = gq.contiguous()
         gh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        L = _lib.load()
+        row_ws = torch.empty(M * (A + 1), dtype=torch.float32, device=h.device)
+        defer = need_w and WeightGradSink.usable((wa, wv))
         gwa = torch.empty_like(wa) if need_w else None
         gwv = torch.empty_like(wv) if need_w else None
-        row_ws = torch.empty(M * (A + 1), dtype=torch.float32, device=h.device)
-        _lib.check(_lib.load().b2rl_dueling_backward(
-            h.data_ptr(), gq.data_ptr(), M, H, wa.data_ptr(), A, wv.data_ptr(),
-            gh.data_ptr() if gh is not None else None, gwa.data_ptr() if need_w else None,
-            gwv.data_ptr() if need_w else None, row_ws.data_ptr(), _stream()))
+        # row pass (dL/dh + the per-row table) on this stream; the column pass (dL/dW) here or on the sink's stream
+        _lib.check(L.b2rl_dueling_backward(h.data_ptr(), gq.data_ptr(), M, H, wa.data_ptr(), A, wv.data_ptr(),
+                                           gh.data_ptr() if gh is not None else None,
+                                           None if (defer or not need_w) else gwa.data_ptr(),
+                                           None if (defer or not need_w) else gwv.data_ptr(), row_ws.data_ptr(), _stream()))
+        if defer:
+            sink = _SINK
+
+            def deferred():
+                _lib.check(L.b2rl_dueling_backward_w(h.data_ptr(), row_ws.data_ptr(), M, H, A, gwa.data_ptr(),
+                                                     gwv.data_ptr(), _stream()))
+                sink.accumulate(wa, gwa)
+                sink.accumulate(wv, gwv)
+            sink.submit(deferred, keep=(h, row_ws, gwa, gwv))
+            return gh, None, None
         return gh, gwa, gwv
 
 

@@ -272,6 +272,10 @@ int b2rl_dueling_forward(const float* h_dev, int64_t M, int64_t H, const float* 
 int b2rl_dueling_backward(const float* h_dev, const float* gq_dev, int64_t M, int64_t H, const float* wa_dev,
                           int64_t A, const float* wv_dev, float* gh_dev, float* gwa_dev, float* gwv_dev,
                           float* row_ws_dev, void* stream);
+/* The weight-gradient half alone, from the row table a previous b2rl_dueling_backward (with gwa_dev = NULL)
+ * left in row_ws_dev: lets the caller run it on another stream than the dL/dh half. */
+int b2rl_dueling_backward_w(const float* h_dev, const float* row_ws_dev, int64_t M, int64_t H, int64_t A,
+                            float* gwa_dev, float* gwv_dev, void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py's
  * `gpu_launches`). */
