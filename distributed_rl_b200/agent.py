@@ -335,9 +335,10 @@ class GraphAgent(nn.Module):
         finally:
             self._pack_cache = None
 
-    def prepack_heads(self):
+    def prepack_heads(self, transposed: bool = False):
         """Fill the packed-operand cache (inside packed_heads_cache()) without running a forward pass, so
-        that passes issued on several streams afterwards only read it."""
+        that passes issued on several streams afterwards only read it.  transposed=True prepares the W^T
+        operand the input-gradient GEMM of a later backward pass needs (entry "bwdT")."""
         if self._pack_cache is None or not (self.dense_3xtf32 and self.fuse_sibling_heads):
             return
         from .linear import _pack_pieces
@@ -346,7 +347,8 @@ class GraphAgent(nn.Module):
             names = (duel["adv"], duel["val"]) if duel is not None else group
             ws = [next(iter(getattr(self, n).children())).weight for n in names]
             if ws[0].is_cuda and not any(w.shape[0] % 32 for w in ws[:-1]):
-                self._pack_cache.setdefault(group, {})["fwd"] = _pack_pieces([w.detach() for w in ws], False, True)
+                self._pack_cache.setdefault(group, {})["bwdT" if transposed else "fwd"] = \
+                    _pack_pieces([w.detach() for w in ws], transposed, True)
 
     def first_conv_node(self):
         """Name of the CNN2D node fed by external input 0, if it starts with the Atari conv_1."""

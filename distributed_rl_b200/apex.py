@@ -396,23 +396,49 @@ class Learner:
             self._pack2 = R.Conv1Pack(2, self.device, c_out)     # online + target in one pass over s'
         return True
 
-    def _forward_backward_fused(self, idx, action, reward, done, weight):
-        """Same maths as _forward_backward, but s and s' are never staged as uint8/fp32 batches:
-        conv_1 reads the sampled rows straight from the replay payload (b2rl_conv1_fused)."""
-        st = self.memory.store
+    def _streams(self):
+        if not hasattr(self, "_fork"):
+            self._fork = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device),
+                          torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event())
+            self._ev_pk, self._ev_tg, self._ev_upd = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        return self._fork
+
+    def _pack_conv1(self):
         w_on = getattr(self.model, self._conv_name).conv_1.weight
         w_tg = getattr(self.target_model, self._conv_name).conv_1.weight
         self._pack1.pack(0, w_on)
         self._pack2.pack(0, w_on)
         self._pack2.pack(1, w_tg)
+
+    def _pack_conv1_async(self):
+        """The conv_1 weight packs of this step on a side stream (they only depend on the weights): they overlap
+        the tree sample + scalar gather at the start of the step.  Returns the event the conv_1 launch waits for."""
+        s1 = self._streams()[0]
+        cur = torch.cuda.current_stream(self.device)
+        self._ev_pk.record(cur)
+        s1.wait_event(self._ev_pk)
+        with torch.cuda.stream(s1):
+            self._pack_conv1()
+            self._ev_pk.record(s1)
+        return self._ev_pk
+
+    def _forward_backward_fused(self, idx, action, reward, done, weight, packs_done=None, update_tree=False):
+        """Same maths as _forward_backward, but s and s' are never staged as uint8/fp32 batches:
+        conv_1 reads the sampled rows straight from the replay payload (b2rl_conv1_fused).
+        `packs_done`: event after which the conv_1 weight packs are valid (None: pack here).
+        `update_tree`: write the new priorities back on a side stream as soon as the target kernel has produced
+        them (overlapping backward); the caller then waits for `self._ev_upd` instead of calling store.update."""
+        st = self.memory.store
+        w_on = getattr(self.model, self._conv_name).conv_1.weight
+        if packs_done is None:
+            self._pack_conv1()
+        else:
+            torch.cuda.current_stream(self.device).wait_event(packs_done)
         with self.model.packed_heads_cache():     # the online weights are packed once for both passes
             if self.cfg.PARALLEL_FORWARDS:
                 # The three passes are independent until the target kernel: fork them onto three streams
                 # (captured as parallel branches of the step's CUDA graph) so their small kernels overlap.
-                if not hasattr(self, "_fork"):
-                    self._fork = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device),
-                                  torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event())
-                s1, s2, e0, e1, e2 = self._fork
+                s1, s2, e0, e1, e2 = self._streams()
                 cur = torch.cuda.current_stream(self.device)
                 self.model.prepack_heads()
                 with torch.no_grad():
@@ -423,6 +449,7 @@ class Learner:
                 with torch.no_grad():
                     with torch.cuda.stream(s1):
                         qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
+                        self.model.prepack_heads(transposed=True)   # W^T operand of the heads' dgrad, off the main branch
                         e1.record(s1)
                     with torch.cuda.stream(s2):
                         qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
@@ -441,6 +468,14 @@ class Learner:
         notdone = 1.0 - done.to(torch.float32)
         out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
                             self.gamma_n, self.cfg.ALPHA)
+        if update_tree:      # priority write-back (one CTA) next to backward instead of after the optimizer
+            s2 = self._streams()[1]
+            cur = torch.cuda.current_stream(self.device)
+            self._ev_tg.record(cur)
+            s2.wait_event(self._ev_tg)
+            with torch.cuda.stream(s2):
+                st.update(idx, out["prio"])
+                self._ev_upd.record(s2)
         if self.cfg.DEFERRED_WGRAD and self._fused_optim:      # grads are pre-allocated and zeroed by the optimizer
             if not hasattr(self, "_sink"):
                 from .linear import WeightGradSink
@@ -476,18 +511,24 @@ class Learner:
                 # (the reference's own max_weight is up to 16 minibatches stale, APE_X/ReplayMemory.py:61-67).
                 mw_work = self._D.all_reduce_max_(st.max_weight(self.cfg.BETA, out=self._max_w), async_op=True)
                 max_w = self._max_w_use
+            side = fused_conv1 and self.cfg.PARALLEL_FORWARDS
+            packs_done = self._pack_conv1_async() if side else None
             idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
             if fused_conv1:
                 if not hasattr(self, "_small"):
                     self._small = st.alloc_batch(B, ("action", "reward", "done"))
                 b = st.gather(idx, self._small)        # scalar fields only; frames go through conv1_fused
-                out = self._forward_backward_fused(idx, b["action"].to(torch.int64), b["reward"], b["done"], w)
+                out = self._forward_backward_fused(idx, b["action"].to(torch.int64), b["reward"], b["done"], w,
+                                                   packs_done=packs_done, update_tree=side)
             else:
                 b = st.gather(idx)
                 out = self._forward_backward(b["state"], b["action"].to(torch.int64), b["reward"],
                                              b["next_state"], b["done"], w)
             info = self.step()
-            st.update(idx, out["prio"])
+            if side:
+                torch.cuda.current_stream(self.device).wait_event(self._ev_upd)
+            else:
+                st.update(idx, out["prio"])
             if mw_work is not None:
                 mw_work.wait()
                 self._max_w_use.copy_(self._max_w)

@@ -146,6 +146,7 @@ class _Linear3x(torch.autograd.Function):
                 cache["fwd"] = b
         y = gemm_packed(split_pack(x, False, False), b, M, N, K)
         ctx.save_for_backward(x, *ws)
+        ctx.cache = cache
         return y
 
     @staticmethod
@@ -157,7 +158,8 @@ class _Linear3x(torch.autograd.Function):
         gx, gws = None, [None] * len(ws)
         if ctx.needs_input_grad[0]:
             # dx[M][K] = gy[M][N] @ W[N][K]: contraction over N, the B operand is W^T ([K rows][N])
-            gx = gemm_packed(split_pack(gy, False, False), _pack_pieces(ws, True, True), M, K, N)
+            bt = ctx.cache.get("bwdT") if ctx.cache is not None else None     # prepared ahead (GraphAgent.prepack_heads)
+            gx = gemm_packed(split_pack(gy, False, False), bt if bt is not None else _pack_pieces(ws, True, True), M, K, N)
         if any(ctx.needs_input_grad[2:]):
             # dW[N][K] = gy^T[N][M] @ x[M][K]: contraction over M
             def wgrad():
