@@ -44,8 +44,8 @@ class _ConvSplitBackward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        from .linear import WeightGradSink, _SINK  # noqa: F401  (module attribute read at call time below)
         from . import linear as _lin
+        WeightGradSink = _lin.WeightGradSink
         x, w = ctx.saved_tensors
         stride, padding = ctx.sp
         bw = torch.ops.aten.convolution_backward

@@ -48,6 +48,32 @@ def _worker(rank, world, port, q):
         dist.all_gather(g, l)
         ok = ok and bool(torch.allclose(p.grad, sum(g) / world))
     out["overlap_ok"] = ok
+    # 1c. early gradients that bypass AccumulateGrad (linear.WeightGradSink): the sink's on_ready callback
+    #     stands in for the autograd hook and launches the early all-reduce
+    lin3 = torch.nn.Sequential(torch.nn.Linear(4, 3, bias=False), torch.nn.Linear(3, 2, bias=False))
+    b3 = D.FlatGradBucket(lin3.parameters())
+    b3.enable_overlap([lin3[1].weight])
+
+    class _Sink:                       # the part of WeightGradSink the bucket uses
+        on_ready = {}
+    b3.attach_sink(_Sink)
+    w_early = lin3[1].weight
+    h3 = lin3[0](x)
+    gw_early = torch.ones(5, 2).T @ h3.detach()            # d(sum)/dW of the last layer, computed "elsewhere"
+    torch.autograd.backward(h3 @ w_early.detach().T, torch.ones(5, 2))   # autograd only sees the late layer
+    w_early.grad.add_(gw_early)
+    _Sink.on_ready[id(w_early)](w_early)                   # what sink.accumulate() does after the add
+    local3 = [p.grad.clone() for p in lin3.parameters()]   # the early part may already be reduced in place: compare sums
+    b3.finish()
+    ref3 = torch.nn.Sequential(torch.nn.Linear(4, 3, bias=False), torch.nn.Linear(3, 2, bias=False))
+    ref3.load_state_dict(lin3.state_dict())
+    ref3(x).sum().backward()
+    ok3 = True
+    for p, r in zip(lin3.parameters(), ref3.parameters()):
+        g = [torch.zeros_like(r.grad) for _ in range(world)]
+        dist.all_gather(g, r.grad)
+        ok3 = ok3 and bool(torch.allclose(p.grad, sum(g) / world, atol=1e-6))
+    out["sink_ok"] = ok3
     # 2. priority-max reduction: shard-local IS weights / global max == single-replay formula
     n, beta = 1024, 0.4
     rng = np.random.default_rng(100 + rank)
@@ -91,6 +117,7 @@ def test_world2_gloo_data_parallel_logic():
     for r in (0, 1):
         assert res[r]["bucket_ok"] and res[r]["views_ok"] and res[r]["isw_ok"] and res[r]["shard_ok"], res[r]
         assert res[r]["overlap_ok"], res[r]
+        assert res[r]["sink_ok"], res[r]
     assert res[0]["mw"] == res[1]["mw"]
 
 
