@@ -49,7 +49,7 @@ class WeightGradSink:
 
     def accumulate(self, param, grad):
         """(side stream) param.grad += grad, then the parameter's ready callback."""
-        param.grad.add_(grad.view_as(param.grad) if grad.shape == param.grad.shape else grad)
+        param.grad.add_(grad)
         cb = self.on_ready.get(id(param))
         if cb is not None:
             cb(param)

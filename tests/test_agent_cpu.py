@@ -1,0 +1,75 @@
+"""Host-side logic of the fused-head paths (no GPU): graph pattern matching in GraphAgent, CPU fall-through of the
+fused flags, the conv split-backward function without a sink, hostmem's topology parsing."""
+import os
+
+import pytest
+
+torch = pytest.importorskip("torch")
+
+
+def _agents():
+    from distributed_rl_b200.agent import GraphAgent
+    from distributed_rl_b200.apex import default_apex_model
+    from distributed_rl_b200.r2d2 import default_r2d2_model
+    from distributed_rl_b200.impala import default_impala_model
+    return GraphAgent, default_apex_model, default_r2d2_model, default_impala_model
+
+
+def test_dueling_pattern_is_found_in_apex_and_r2d2_not_in_impala():
+    GraphAgent, apex_m, r2d2_m, impala_m = _agents()
+    a = GraphAgent(apex_m())
+    (g, d), = a._dueling.items()
+    assert (d["adv"], d["val"], d["out"]) == ("module02", "module02_1", "module04")
+    assert set(d["inner"]) == {"module02", "module02_1", "module03", "module03_1"}
+    r = GraphAgent(r2d2_m())
+    (g, d), = r._dueling.items()
+    assert (d["adv"], d["val"], d["out"]) == ("module03", "module03_1", "module05")
+    assert GraphAgent(impala_m())._dueling == {}
+
+
+def test_pattern_rejects_lookalikes():
+    GraphAgent, apex_m, _, _ = _agents()
+    m = apex_m()
+    m["module03_1"]["prevNodeNames"] = ["module02_1"]          # mean over the value head: not the dueling combine
+    assert GraphAgent(m)._dueling == {}
+    m = apex_m()
+    m["module02"]["output"] = True                             # an inner node is also a network output
+    assert GraphAgent(m)._dueling == {}
+    m = apex_m()
+    m["module02_1"]["fSize"] = [512, 2]                        # "value" head with two outputs
+    assert GraphAgent(m)._dueling == {}
+
+
+def test_fused_flags_fall_through_on_cpu_and_split_backward_matches_autograd():
+    GraphAgent, apex_m, _, _ = _agents()
+    torch.manual_seed(0)
+    m = GraphAgent(apex_m())
+    x = torch.rand(3, 4, 84, 84)
+    ref = m([x])[0]
+    m.fused_dueling_tail = m.dense_3xtf32 = True               # CUDA-only paths: must not be taken for CPU tensors
+    with m.packed_heads_cache():
+        m.prepack_heads()
+        out = m([x])[0]
+    assert torch.equal(out, ref)
+    # _ConvSplitBackward without an active sink == plain conv backward
+    from distributed_rl_b200.agent import _ConvSplitBackward
+    w = torch.randn(8, 4, 3, 3, requires_grad=True)
+    xi = torch.randn(2, 4, 9, 9, requires_grad=True)
+    gy = torch.randn(2, 8, 4, 4)
+    _ConvSplitBackward.apply(xi, w, (2, 2), (0, 0)).backward(gy)
+    gx, gw = xi.grad.clone(), w.grad.clone()
+    xi.grad = w.grad = None
+    torch.nn.functional.conv2d(xi, w, None, (2, 2), (0, 0)).backward(gy)
+    torch.testing.assert_close(gx, xi.grad)
+    torch.testing.assert_close(gw, w.grad)
+
+
+def test_hostmem_cpulist_parsing_and_unbound_fallback():
+    from distributed_rl_b200 import hostmem
+    assert hostmem._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem._parse_cpulist("") == set()
+    assert hostmem.gpu_node_cpus("cuda:0") is None or isinstance(hostmem.gpu_node_cpus("cuda:0"), set)
+    before = os.sched_getaffinity(0)
+    with hostmem.on_gpu_node("cuda:0") as bound:               # no GPU here: must be a no-op
+        assert bound in (False, True)
+    assert os.sched_getaffinity(0) == before
