@@ -252,21 +252,32 @@ class _Conv1Gathered(torch.autograd.Function):
     fused_wgrad = True
 
     @staticmethod
-    def forward(ctx, weight, frames, idx, pack, mem_format, store=None, y_pre=None):
+    def forward(ctx, weight, frames, idx, pack, mem_format, store=None, y_pre=None, relu=False):
+        """relu=True: the kernel's epilogue applies the ReLU that follows conv_1 and backward applies its mask
+        inside the wgrad kernel (the caller must then skip the network's own ReLU: forward_from_conv1(y, True))."""
         ctx.frames, ctx.store, ctx.mem_format, ctx.wshape = frames, store, mem_format, weight.shape
-        ctx.has_idx = idx is not None
-        ctx.save_for_backward(idx if idx is not None else torch.empty(0, dtype=torch.int64, device=frames.device))
+        ctx.has_idx, ctx.relu = idx is not None, bool(relu)
+        idx_t = idx if idx is not None else torch.empty(0, dtype=torch.int64, device=frames.device)
         if y_pre is not None:
-            return y_pre.view_as(y_pre)
-        return R.conv1_fused(frames, idx, pack, relu=False)[0]
+            y = y_pre.view_as(y_pre)
+        else:
+            y = R.conv1_fused(frames, idx, pack, relu=bool(relu))[0]
+        if relu:
+            ctx.save_for_backward(idx_t, y)
+        else:
+            ctx.save_for_backward(idx_t)
+        return y
 
     @staticmethod
     def backward(ctx, gy):
-        (idx,) = ctx.saved_tensors
+        idx = ctx.saved_tensors[0]
+        y = ctx.saved_tensors[1] if ctx.relu else None
         if _Conv1Gathered.fused_wgrad:
             # fused gather + wgrad on the tensor cores: the sampled rows are never staged (csrc/conv1_wgrad.cu)
-            gw = R.conv1_wgrad(ctx.frames, idx if ctx.has_idx else None, gy)
-            return gw, None, None, None, None, None, None
+            gw = R.conv1_wgrad(ctx.frames, idx if ctx.has_idx else None, gy, relu_y=y)
+            return (gw,) + (None,) * (len(ctx.needs_input_grad) - 1)
+        if y is not None:
+            gy = gy * (y > 0)
         if not ctx.has_idx:
             x = ctx.frames
         elif ctx.store is not None:    # TMA bulk gather straight from the replay payload
@@ -275,7 +286,7 @@ class _Conv1Gathered(torch.autograd.Function):
             x = ctx.frames.index_select(0, idx)
         xf = (x.to(torch.float32) / 255.0).contiguous(memory_format=ctx.mem_format)
         gw = torch.nn.grad.conv2d_weight(xf, ctx.wshape, gy.contiguous(memory_format=ctx.mem_format), stride=4)
-        return gw, None, None, None, None, None, None
+        return (gw,) + (None,) * (len(ctx.needs_input_grad) - 1)
 
 
 class Learner:
@@ -454,8 +465,8 @@ class Learner:
                     with torch.cuda.stream(s2):
                         qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
                         e2.record(s2)
-                y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
-                q = self.model.forward_from_conv1(y, False)[0]                       # :78
+                y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st, None, True)
+                q = self.model.forward_from_conv1(y, True)[0]                        # :78 (ReLU in the conv_1 epilogue)
                 cur.wait_event(e1)
                 cur.wait_event(e2)
             else:
@@ -463,8 +474,8 @@ class Learner:
                     y_on, y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True)
                     qn_online = self.model.forward_from_conv1(y_on, True)[0]        # :87
                     qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
-                y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st)
-                q = self.model.forward_from_conv1(y, False)[0]                       # :78
+                y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st, None, True)
+                q = self.model.forward_from_conv1(y, True)[0]                        # :78 (ReLU in the conv_1 epilogue)
         notdone = 1.0 - done.to(torch.float32)
         out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
                             self.gamma_n, self.cfg.ALPHA)

@@ -107,6 +107,7 @@ struct Params {
   const int64_t* idx;        // sampled rows, or nullptr for rows 0..n-1
   int64_t n, capacity;
   const float* gy;           // [n][400][C_OUT] fp32 (NHWC)
+  const float* y;            // optional conv_1 output after ReLU, same layout: dL/dy is taken as gy * (y > 0); else nullptr
   float* partial;            // [gridDim.x][C_OUT][256]
   long long* dbg;            // optional [16] cycle counters of CTA 0 (B2RL_CONV1_DBG=1), else nullptr
 };
@@ -197,11 +198,17 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
       uint4 m = make_uint4(0u, 0u, 0u, 0u);
       for (int64_t k = first; k < P.n; k += stride) {
         const uint4* g = reinterpret_cast<const uint4*>(P.gy + k * (int64_t)(POS * C_OUT));
+        const float4* yk = P.y ? reinterpret_cast<const float4*>(P.y + k * (int64_t)(POS * C_OUT)) : nullptr;
 #pragma unroll
         for (int i = 0; i < (POS * C_OUT / 4 + 255) / 256; ++i) {
           const int e = pt + 256 * i;
           if (e < POS * C_OUT / 4) {
-            const uint4 v = g[e];
+            uint4 v = g[e];
+            if (yk) {                                    // ReLU mask of the fused forward
+              const float4 yv = yk[e];
+              v.x = yv.x > 0.0f ? v.x : 0u; v.y = yv.y > 0.0f ? v.y : 0u;
+              v.z = yv.z > 0.0f ? v.z : 0u; v.w = yv.w > 0.0f ? v.w : 0u;
+            }
             m.x = max(m.x, v.x & 0x7FFFFFFFu); m.y = max(m.y, v.y & 0x7FFFFFFFu);
             m.z = max(m.z, v.z & 0x7FFFFFFFu); m.w = max(m.w, v.w & 0x7FFFFFFFu);
           }
@@ -282,13 +289,24 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
       const int total = (int)n_items * CHUNKS;
       auto load_chunk = [&](int at, float (&v)[4][4]) {
         const int j = at & 3;
-        const float* g = P.gy + (first + (int64_t)(at >> 2) * stride) * (int64_t)(POS * C_OUT) + co;
+        const int64_t base = (first + (int64_t)(at >> 2) * stride) * (int64_t)(POS * C_OUT) + co;
+        const float* g = P.gy + base;
         const int u0 = (j < CHUNKS - 1) ? uh * 4 : uh, nu = (j < CHUNKS - 1) ? 4 : 1;
 #pragma unroll
         for (int uu = 0; uu < 4; ++uu) {
           const int p = j * KCHUNK + (u0 + uu) * 16 + 4 * pq;
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[uu][i] = (uu < nu && p < POS) ? g[(int64_t)(p + i) * C_OUT] : 0.0f;
+        }
+        if (P.y) {                                       // ReLU mask of the fused forward
+          const float* yk = P.y + base;
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu) {
+            const int p = j * KCHUNK + (u0 + uu) * 16 + 4 * pq;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (uu < nu && p < POS && !(yk[(int64_t)(p + i) * C_OUT] > 0.0f)) v[uu][i] = 0.0f;
+          }
         }
       };
       float v[4][4], vn[4][4];
@@ -432,13 +450,14 @@ extern "C" int64_t b2rl_conv1_wgrad_workspace_floats(int32_t c_out) {
 }
 
 extern "C" int b2rl_conv1_wgrad(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
-                                const float* gy_dev, int32_t c_out, float* workspace_dev, float* gw_dev,
-                                int32_t accumulate, void* stream) {
+                                const float* gy_dev, const float* y_relu_dev, int32_t c_out, float* workspace_dev,
+                                float* gw_dev, int32_t accumulate, void* stream) {
   B2RL_REQUIRE(n >= 1, "n must be positive");
   B2RL_REQUIRE(frames_dev && gy_dev && workspace_dev && gw_dev, "null argument");
   B2RL_REQUIRE(c_out == 16 || c_out == 32, "c_out must be 16 or 32");
   B2RL_REQUIRE(capacity >= 1, "capacity must be positive");
-  B2RL_REQUIRE(((uintptr_t)frames_dev % 16 == 0) && ((uintptr_t)gy_dev % 16 == 0), "frames and gy must be 16-byte aligned");
+  B2RL_REQUIRE(((uintptr_t)frames_dev % 16 == 0) && ((uintptr_t)gy_dev % 16 == 0) && ((uintptr_t)y_relu_dev % 16 == 0),
+               "frames, gy and y must be 16-byte aligned");
   int dev = 0;
   B2RL_CUDA(cudaGetDevice(&dev));
   static int sms[64] = {0};
@@ -452,7 +471,8 @@ extern "C" int b2rl_conv1_wgrad(const uint8_t* frames_dev, int64_t capacity, con
   for (int64_t off = 0; off < n; off += per_launch) {
     const int64_t m = (n - off < per_launch) ? n - off : per_launch;
     conv1w::Params P{frames_dev, idx_dev ? idx_dev + off : nullptr, m, capacity,
-                     gy_dev + off * (int64_t)(conv1w::POS * c_out), workspace_dev, dbg_buf};
+                     gy_dev + off * (int64_t)(conv1w::POS * c_out),
+                     y_relu_dev ? y_relu_dev + off * (int64_t)(conv1w::POS * c_out) : nullptr, workspace_dev, dbg_buf};
     if (!idx_dev) P.frames = frames_dev + off * conv1w::FRAME_BYTES, P.capacity = capacity - off;
     const unsigned grid = (unsigned)((m < sms[dev & 63]) ? m : sms[dev & 63]);
     B2RL_CUDA(c_out == 32 ? wgrad_launch<32>(P, grid, st) : wgrad_launch<16>(P, grid, st));

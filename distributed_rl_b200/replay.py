@@ -405,15 +405,19 @@ _wgrad_ws = {}
 
 
 def conv1_wgrad(frames: torch.Tensor, idx, gy: torch.Tensor, out: torch.Tensor | None = None,
-                accumulate: bool = False) -> torch.Tensor:
+                accumulate: bool = False, relu_y: torch.Tensor | None = None) -> torch.Tensor:
     """dL/dW of conv_1 from the sampled uint8 rows and dL/dy, without staging the rows (b2rl_conv1_wgrad).
     frames: uint8 (rows, 4, 84, 84) contiguous; idx: int64[n] or None; gy: (n, c_out, 20, 20) fp32
-    (made channels_last if it is not) -> (c_out, 4, 8, 8) fp32."""
+    (made channels_last if it is not) -> (c_out, 4, 8, 8) fp32.  relu_y: the post-ReLU output of
+    conv1_fused(relu=True) for the same rows; gy is then dL/d(relu output) and is masked by (y > 0) in the kernel."""
     assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames[0].numel() == FRAME_STACK_BYTES
     n = frames.shape[0] if idx is None else idx.numel()
     c_out = gy.shape[1]
     assert gy.shape == (n, c_out, 20, 20) and gy.dtype == torch.float32
     gy = gy.contiguous(memory_format=torch.channels_last)
+    if relu_y is not None:
+        assert relu_y.shape == gy.shape and relu_y.dtype == torch.float32
+        relu_y = relu_y.contiguous(memory_format=torch.channels_last)
     dev = frames.device
     key = (dev, c_out)
     if key not in _wgrad_ws:
@@ -424,6 +428,6 @@ def conv1_wgrad(frames: torch.Tensor, idx, gy: torch.Tensor, out: torch.Tensor |
         accumulate = False
     assert out.is_contiguous() and out.numel() == c_out * 256
     check(_lib.load().b2rl_conv1_wgrad(frames.data_ptr(), frames.shape[0], None if idx is None else idx.data_ptr(), n,
-                                       gy.data_ptr(), c_out, _wgrad_ws[key].data_ptr(), out.data_ptr(),
-                                       int(bool(accumulate)), _stream_ptr(dev)))
+                                       gy.data_ptr(), None if relu_y is None else relu_y.data_ptr(), c_out,
+                                       _wgrad_ws[key].data_ptr(), out.data_ptr(), int(bool(accumulate)), _stream_ptr(dev)))
     return out

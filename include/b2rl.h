@@ -221,13 +221,15 @@ int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t*
 /* Weight gradient of conv_1 fused with the gather (the backward half of b2rl_conv1_fused;
  * loss.backward() in APE_X/Learner.py:123-138 for baseline/baseNetwork.py:165-172's first layer):
  *   gw[co][c][ky][kx] (+)= (1/255) * sum_{k,oy,ox} gy[k][oy][ox][co] * frames[idx[k]][c][4oy+ky][4ox+kx]
- * gy_dev: [n][20][20][c_out] fp32 (NHWC); gw_dev: [c_out][4][8][8] fp32; workspace_dev:
+ * gy_dev: [n][20][20][c_out] fp32 (NHWC); y_relu_dev: NULL, or the post-ReLU output of b2rl_conv1_fused(relu = 1)
+ * for the same rows — gy is then the gradient w.r.t. that output and is masked by (y > 0) on the fly (the
+ * ReLU's backward); gw_dev: [c_out][4][8][8] fp32; workspace_dev:
  * b2rl_conv1_wgrad_workspace_floats(c_out) floats of scratch (per-SM partial sums, summed in fp64 in a
  * fixed order: the result is deterministic).  idx_dev may be NULL (rows 0..n-1). */
 int64_t b2rl_conv1_wgrad_workspace_floats(int32_t c_out);
 int b2rl_conv1_wgrad(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
-                     const float* gy_dev, int32_t c_out, float* workspace_dev, float* gw_dev,
-                     int32_t accumulate, void* stream);
+                     const float* gy_dev, const float* y_relu_dev, int32_t c_out, float* workspace_dev,
+                     float* gw_dev, int32_t accumulate, void* stream);
 
 /* Learner.step (APE_X/Learner.py:123-138; IMPALA/Learner.py:258-266 without the clipping) with
  * torch.optim.RMSprop's update (baseline/utils.py getOptim :124-130; centered for Ape-X,

@@ -125,3 +125,9 @@ def test_conv1_wgrad_matches_fp64(R, c_out, n):
     torch.testing.assert_close(acc, 2 * gw2, rtol=1e-6, atol=0)
     # deterministic
     assert torch.equal(R.conv1_wgrad(fr, torch.from_numpy(idx).cuda(), gyc), gw)
+    # ReLU mask of the fused forward: gy * (y > 0) applied inside the kernel
+    yk = torch.relu(torch.randn(n, c_out, 20, 20, generator=g))
+    gwm = R.conv1_wgrad(fr, torch.from_numpy(idx).cuda(), gyc,
+                        relu_y=yk.cuda().contiguous(memory_format=torch.channels_last))
+    refm = _wgrad_ref(frames, idx, gy * (yk > 0))
+    assert (gwm.double().cpu() - refm).abs().max().item() <= 2e-6 * max(refm.abs().max().item(), 1e-30)
