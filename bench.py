@@ -7,17 +7,20 @@ target + priority update, inside a full learner step) on N B200s.
 Workload (BASELINE.json configs[1]): Ape-X DQN, 2^20-slot
 device-resident sum-tree per GPU, synthetic (4,84,84) uint8 frame stacks (59.2 GB
 payload per GPU), batch 512 per GPU.  One "step" = one learner step:
-  tree sample (512) -> IS weights -> TMA gather of s, s', a, r, done ->
-  Q(s), Q(s'), Qbar(s') -> fused double-DQN n-step target / clipped TD /
-  priority / dLoss/dQ -> backward -> centered RMSprop -> tree priority write-back
+  tree sample (512) -> IS weights -> TMA gather of a, r, done (s and s' are read by the fused
+  gather + conv_1 kernels straight from the replay payload) -> Q(s), Q(s'), Qbar(s') ->
+  fused double-DQN n-step target / clipped TD / priority / dLoss/dQ -> backward ->
+  centered RMSprop -> tree priority write-back
 N > 1: one process per GPU, replay sharded (2^20 slots each, weak scaling),
 NCCL all-reduce of the gradients (AVG) and of the max IS weight (MAX) — the
 only inter-GPU traffic.
 
 `value` = transitions/s with everything resident in HBM, the whole step replayed
-as one CUDA graph.  `e2e` = the same loop through the public Python API with
-HOST buffers: every step ingests 512 new transitions from pinned host memory
-(Replay.push_arrays -> b2rl_replay_push) and reads the step's scalars back.
+as one CUDA graph (with parallel branches: the three forward passes, the weight
+gradients, the tree update).  `e2e` = the same loop through the public Python API
+with HOST buffers: every step ingests 512 new transitions from pinned host memory
+(Replay.begin_ingest / commit_ingest -> b2rl_replay_reserve / copy_payload / commit,
+the copy overlapping the step) and reads the step's scalars back.
 
 --impl reference times the CPU port of the reference learner loop
 (oracle/cpu_learner.py; the reference is pure Python and /root/reference does not
@@ -186,8 +189,9 @@ def workload_config(args, world):
             "record_bytes": ALG_BYTES_PER_TRANSITION_GATHER,
             "parallelism": f"replay-sharded dp{world}" if world > 1 else "single GPU",
             "l2": "inputs >> L2: every step gathers random rows of a 59 GB payload (no L2 flush needed)",
-            "network": "dueling DQN of cfg/ape_x.json; conv_1 fused with the gather on tcgen05 (int8 digits, fp32-exact), "
-                       "rest in PyTorch at its default precision (fp32 matmul, TF32 cuDNN convs) = what the reference runs"}
+            "network": "dueling DQN of cfg/ape_x.json; conv_1 forward and weight gradient fused with the gather on tcgen05 "
+                       "(int8 digits, fp32-exact), dense heads as 3xTF32 tcgen05 GEMMs at fp32 accuracy, fused dueling tail; "
+                       "conv_2/conv_3 in cuDNN at PyTorch's default precision (TF32 convs) = what the reference runs"}
 
 
 # --------------------------------------------------------------------------- #
