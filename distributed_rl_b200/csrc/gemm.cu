@@ -154,7 +154,7 @@ k_gemm_tf32x3(const __grid_constant__ Params P) {
   const int64_t per = (P.k_chunks + P.splits - 1) / P.splits;
   const int64_t k0 = (int64_t)blockIdx.z * per;
   const int64_t k1 = (k0 + per < P.k_chunks) ? k0 + per : P.k_chunks;
-  const int64_t nk = k1 - k0;   // may be <= 0 for a trailing split: then the CTA only participates in setup
+  const int64_t nk = k1 - k0;   // > 0: the host never launches an empty trailing split (gemm_splits)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
