@@ -13,7 +13,6 @@ from __future__ import annotations
 import threading
 from dataclasses import dataclass, field
 
-import numpy as np
 import torch
 
 from . import replay as R
