@@ -63,7 +63,8 @@ int b2rl_replay_destroy(b2rl_replay* h);
  * the ring head (next slot to be written). Host-side, no sync. */
 int b2rl_replay_size(const b2rl_replay* h, int64_t* size, int64_t* capacity, int64_t* head);
 
-/* Device base pointer of payload field f (capacity x field_bytes[f] bytes). */
+/* Device base pointer of payload field f (capacity x field_bytes[f] bytes): the storage behind
+ * PER.memory / Tree.data (baseline/PER.py:7-28), exposed so that consumers (b2rl_conv1_fused) read rows in place. */
 int b2rl_replay_field_ptr(const b2rl_replay* h, int32_t field, void** ptr_dev);
 
 /* PER.push (baseline/PER.py:69-75) / PrioritizedMemory.push
@@ -77,7 +78,8 @@ int b2rl_replay_field_ptr(const b2rl_replay* h, int32_t field, void** ptr_dev);
 int b2rl_replay_push(b2rl_replay* h, const void* const* fields_src, const float* prios,
                      int64_t n, void* stream);
 
-/* Pipelined ingest — the same PER.push, split so that the host->device copy of the NEXT batch of
+/* Pipelined ingest — the same PER.push (baseline/PER.py:69-75; drained from Redis by Replay.run,
+ * APE_X/ReplayMemory.py:128-139), split so that the host->device copy of the NEXT batch of
  * records can run on its own stream while the learner step of the current batch computes:
  *   reserve   (learner stream) priorities of the next n ring slots := 0, so the records about to
  *             be overwritten can no longer be sampled; *start_slot receives the first slot
@@ -93,7 +95,8 @@ int b2rl_replay_commit(b2rl_replay* h, const float* prios, int64_t n, void* stre
  * records (priority := 0 so they can never be sampled; size -= delta). */
 int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream);
 
-/* Benchmark / property-test helper (no reference counterpart): fill slots
+/* Benchmark / property-test helper (no reference counterpart; stands in for a replay pre-filled through
+ * PER.push, baseline/PER.py:69-75, with SURVEY.md §8d's synthetic frames): fill slots
  * [0, n) of every field with the counter hash documented in DESIGN.md §4
  * (word w of slot s of field f = lowbias32(seed ^ f*0x9E3779B9 ^ s*2654435761
  * ^ w*2246822519)) and mark them valid.  Priorities are NOT touched: follow
@@ -124,7 +127,7 @@ int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t seed, uint6
                      int64_t n, float beta, const float* max_w_dev, int64_t* idx_out_dev,
                      float* prob_out_dev, float* w_out_dev, void* stream);
 
-/* Same, but the uniforms come from the handle's DEVICE-RESIDENT Philox stream
+/* Same (PER.sample, baseline/PER.py:92-116), but the uniforms come from the handle's DEVICE-RESIDENT Philox stream
  * {seed, counter} (set with b2rl_replay_seed), and the counter is advanced by n
  * on the stream afterwards — so the call can be captured in a CUDA graph and
  * every replay draws fresh numbers.  Draw k of the call uses counter + k. */
@@ -132,7 +135,8 @@ int b2rl_replay_seed(b2rl_replay* h, uint64_t seed, uint64_t counter, void* stre
 int b2rl_tree_sample_stream(b2rl_replay* h, int64_t n, float beta, const float* max_w_dev,
                             int64_t* idx_out_dev, float* prob_out_dev, float* w_out_dev, void* stream);
 
-/* The uniforms b2rl_tree_sample would draw for (seed, rng_offset) — lets a
+/* The uniforms b2rl_tree_sample would draw for (seed, rng_offset) in place of torch.multinomial's generator
+ * (baseline/PER.py:97) — lets a
  * test replay a device-RNG run through the oracle. */
 int b2rl_philox_uniforms(uint64_t seed, uint64_t rng_offset, int64_t n, double* out_dev,
                          void* stream);
@@ -254,7 +258,7 @@ int b2rl_rmsprop_step(float* const* params, float* const* grads, float* const* s
 int64_t b2rl_gemm_packed_floats(int64_t rows, int64_t k, int32_t b_role);
 int b2rl_gemm_split_pack(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
                          int32_t transpose, int32_t b_role, float* out_dev, void* stream);
-/* One piece of an operand (stacked weight matrices): image rows [row_offset, +rows), contraction
+/* One piece of an operand (stacked weight matrices of sibling heads, cfg/ape_x.json:52-71): image rows [row_offset, +rows), contraction
  * [k_offset, +k) of a total_rows x total_k operand; offsets (and inner piece sizes) multiples of 32. */
 int b2rl_gemm_split_pack_into(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
                               int32_t transpose, int32_t b_role, float* out_dev, int64_t total_rows,
@@ -274,7 +278,8 @@ int b2rl_dueling_forward(const float* h_dev, int64_t M, int64_t H, const float* 
 int b2rl_dueling_backward(const float* h_dev, const float* gq_dev, int64_t M, int64_t H, const float* wa_dev,
                           int64_t A, const float* wv_dev, float* gh_dev, float* gwa_dev, float* gwv_dev,
                           float* row_ws_dev, void* stream);
-/* The weight-gradient half alone, from the row table a previous b2rl_dueling_backward (with gwa_dev = NULL)
+/* The weight-gradient half alone (dL/dW of the heads' second layers, cfg/ape_x.json:52-71; part of loss.backward(),
+ * APE_X/Learner.py:123-138), from the row table a previous b2rl_dueling_backward (with gwa_dev = NULL)
  * left in row_ws_dev: lets the caller run it on another stream than the dL/dh half. */
 int b2rl_dueling_backward_w(const float* h_dev, const float* row_ws_dev, int64_t M, int64_t H, int64_t A,
                             float* gwa_dev, float* gwv_dev, void* stream);
