@@ -45,6 +45,7 @@ class ApexConfig:
     TARGET_FREQUENCY: int = 2500
     LEARNER_DEVICE: str = "cuda:0"
     REDIS_SERVER: str = "localhost"
+    LOG_W: str | None = None        # ./weight/<ALG>/<time> (configuration.py:101-109); None: no checkpoints
     OPTIM_INFO: dict = field(default_factory=lambda: {
         "name": "rmsprop", "lr": 0.0000625, "eps": 1.5e-7, "decay": 0, "alpha": 0.95, "momentum": 0,
         "centered": True})
@@ -64,6 +65,7 @@ class ApexConfig:
         kw = {k: getattr(C, k) for k in ("BATCHSIZE", "ACTION_SIZE", "ALPHA", "BETA", "GAMMA", "UNROLL_STEP",
                                          "REPLAY_MEMORY_LEN", "BUFFER_SIZE", "TARGET_FREQUENCY",
                                          "LEARNER_DEVICE", "REDIS_SERVER", "OPTIM_INFO", "MODEL")}
+        kw["LOG_W"] = getattr(C, "LOG_W", None)
         return ApexConfig(**kw)
 
 
@@ -131,7 +133,7 @@ class Replay(threading.Thread):
         self.deque = []            # pre-assembled minibatches (filled on demand)
         self.total_frame = 0
         self._lock = threading.Lock()
-        self._stop = False
+        self._stop_evt = threading.Event()     # NOT `_stop`: that name is threading.Thread's own method
 
     # -- ingest: records are [s, a, R_n, s', done, prio] pickled by the actors ----
     def push_records(self, blobs) -> None:
@@ -140,14 +142,11 @@ class Replay(threading.Thread):
         H2D copy + fused leaf write / path refresh."""
         if not blobs:
             return
+        from .wire import decode_apex
         recs = [pickle.loads(b) for b in blobs]
         n = len(recs)
         st = self._staging(n)        # pinned, on the GPU's NUMA node: the H2D copy is a straight DMA
-        s, ns, a, rw, d, p = (st[k][:n].numpy() for k in ("s", "ns", "a", "r", "d", "p"))
-        for i, r in enumerate(recs):
-            s[i] = np.asarray(r[0], np.uint8).reshape(s.shape[1:])
-            ns[i] = np.asarray(r[3], np.uint8).reshape(ns.shape[1:])
-            a[i], rw[i], d[i], p[i] = int(r[1]), float(r[2]), bool(r[4]), float(r[5])
+        decode_apex(recs, {k: st[k][:n].numpy() for k in ("s", "ns", "a", "r", "d", "p")})
         with self._lock:
             self.store.push([st[k][:n] for k in ("s", "ns", "a", "r", "d")], st["p"][:n])
             st["event"].record(torch.cuda.current_stream(self.device))
@@ -194,20 +193,37 @@ class Replay(threading.Thread):
             self.store.push_commit(p)
         self.total_frame += int(torch.as_tensor(p).numel())
 
+    def stop(self) -> None:
+        """Ask the ingest thread to leave its loop (the reference's daemon thread can only die with the process)."""
+        self._stop_evt.set()
+
     def run(self):
-        """Poll the actors' Redis list like APE_X/ReplayMemory.py:118-161."""
+        """Poll the actors' Redis list like APE_X/ReplayMemory.py:118-161: drain `experience`, push, honour the
+        learner's eviction request (`lock`, :151-160).  Minibatches are assembled on demand by sample()."""
         if self.connect is None:
             return
-        while not self._stop:
-            pipe = self.connect.pipeline()
-            pipe.lrange("experience", 0, -1)
-            pipe.ltrim("experience", -1, 0)
-            data = pipe.execute()[0]
+        from .wire import drain
+        while not self._stop_evt.is_set():
+            data = drain(self.connect, "experience")
             if data:
                 self.push_records(data)
-                self.cond = len(self.store) > 50000
-            else:
+                self.cond = len(self.store) > self.cfg.BUFFER_SIZE
+            if self.lock:
+                self._evict_on_request()
+            if not data:
                 time.sleep(0.002)
+
+    def _evict_on_request(self) -> None:
+        """The `lock` handshake (APE_X/ReplayMemory.py:151-160, APE_X/Learner.py:189-197): once the memory is full,
+        drop queued minibatches and trim to REPLAY_MEMORY_LEN (PER.remove_to_fit, baseline/PER.py:118-127).  The
+        ring already overwrites its oldest slot on push, so there is normally nothing to trim."""
+        if len(self.store) >= self.cfg.REPLAY_MEMORY_LEN:
+            with self._lock:
+                self.deque.clear()
+                over = len(self.store) - self.cfg.REPLAY_MEMORY_LEN
+                if over > 0:
+                    self.store.evict(over)
+        self.lock = False
 
     # -- sampling -------------------------------------------------------------------
     def buffer(self, m: int = 1) -> None:
@@ -239,7 +255,9 @@ class Replay(threading.Thread):
             self.store.update(idx.to(self.device), vals.to(self.device))
 
     def _update(self):
-        return None
+        """Replay._update (:49-59) applies the pending write-backs; here update() has already enqueued them on
+        the stream, so all that is left is to make them visible to the host."""
+        torch.cuda.current_stream(self.device).synchronize()
 
 
 class _Conv1Gathered(torch.autograd.Function):
@@ -305,6 +323,9 @@ class Learner:
         if start_replay and connect is not None:
             self.memory.start()
         self.writer = writer
+        if connect is not None:                  # :41-43 — whatever a previous run left behind is dropped
+            from .wire import wipe_stale_keys
+            wipe_stale_keys(connect)
         self.gamma_n = float(np.float32(0.99 ** self.cfg.UNROLL_STEP))  # hard-coded 0.99, :103
         self._graph = None
         self._world = 1
@@ -555,17 +576,20 @@ class Learner:
             return r
         self.optim.zero_grad(set_to_none=False)
         side = torch.cuda.Stream(self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            for _ in range(3):   # warm-up: lazy inits (cuDNN plans, optimizer state) happen outside capture
-                body()
-        torch.cuda.current_stream(self.device).wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        c0 = lib.b2rl_launch_count()
-        with torch.cuda.graph(g):
-            self._static = body()
-        self.launches_per_step = lib.b2rl_launch_count() - c0   # recorded into the graph, replayed each step
+        # The ingest thread keeps pushing on the same replay handle: hold its lock so that no cudaMalloc /
+        # cudaHostAlloc / copy of that thread lands inside the warm-up or the (global-mode) capture.
+        with self.memory._lock:
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):   # warm-up: lazy inits (cuDNN plans, optimizer state) happen outside capture
+                    body()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            c0 = lib.b2rl_launch_count()
+            with torch.cuda.graph(g):
+                self._static = body()
+            self.launches_per_step = lib.b2rl_launch_count() - c0   # recorded into the graph, replayed each step
         self._graph = g
         g.replay()
         return self._static
@@ -580,8 +604,13 @@ class Learner:
         return {k: v.cpu() for k, v in self.target_model.state_dict().items()}
 
     def run(self, max_steps: int | None = None, log_every: int = 500):
-        """Learner.run (:140-262) — same cadence of target sync (TARGET_FREQUENCY) and
-        parameter publication (every 50 steps) when a Redis connection is present."""
+        """Learner.run (:140-262) with the reference's cadence: wait for BUFFER_SIZE records, announce `Start`,
+        hard target sync every TARGET_FREQUENCY steps, parameter publication every 50, and every `log_every`
+        (500) steps the eviction request (`memory.lock`, :189-191), the `reward` drain + log line (:219-253) and a
+        checkpoint of the online weights (:256-262).  Publication and checkpoints go through ParamPublisher
+        (async D2H into pinned memory), so none of them stalls the learner stream."""
+        from .publish import ParamPublisher
+        from . import wire
         while len(self.memory.memory) <= self.cfg.BUFFER_SIZE:
             time.sleep(0.05)
         if self.connect is not None:
@@ -589,29 +618,46 @@ class Learner:
             self.connect.set("count", pickle.dumps(1))
             self.connect.set("target_state_dict", pickle.dumps(self.target_state_dict))
             self.connect.set("Start", pickle.dumps(True))
-        from .publish import ParamPublisher
         pub = ParamPublisher(self.model, self.connect, "state_dict", "count")
         pub_t = ParamPublisher(self.target_model, self.connect, "target_state_dict", None)
-        self._publishers = (pub, pub_t)
+        ckpt_path = wire.checkpoint_path(self.cfg.LOG_W)
+        ckpt = ParamPublisher(self.model, None, None, None,
+                              on_ready=lambda sd, step: torch.save(sd, ckpt_path)) if ckpt_path else None
+        self._publishers = (pub, pub_t) + ((ckpt,) if ckpt else ())
         step = 0
         t0 = time.time()
         acc = None
+        self.last_log = None
         while max_steps is None or step < max_steps:
             out = self.fused_step()
             step += 1
-            acc = out["scalars"].clone() if acc is None else acc + out["scalars"]
+            tot = torch.cat([out["scalars"], out["p_norm"].reshape(1)])
+            acc = tot.clone() if acc is None else acc + tot
             if step % self.cfg.TARGET_FREQUENCY == 0:
                 self.target_model.updateParameter(self.model, 1)
                 pub_t.snapshot(step)                 # async D2H; published by a later poll()
             if step % 50 == 0:
                 pub.snapshot(step - 50)              # :212-216, without stalling the learner stream
-            pub.poll(); pub_t.poll()
+            for p in self._publishers:
+                p.poll()
             if step % log_every == 0:
-                loss, mean_value, mean_w = (acc / log_every).tolist()
+                self.memory.lock = True              # :189-191 eviction request, served by the ingest thread
+                if self.connect is None or not self.memory.is_alive():
+                    self.memory._evict_on_request()
+                reward, n_rew = wire.drain_rewards(self.connect) if self.connect is not None else (-21.0, 0)
+                loss, mean_value, mean_w, norm = (acc / log_every).tolist()
                 dt = (time.time() - t0) / log_every
-                print(f"step:{step} // mean_value:{mean_value:.3f} // loss:{loss:.5f} // NUM_MEMORY:"
-                      f"{len(self.memory.memory)} // Mean_Weight:{mean_w:.3f} // TIME:{dt:.5f}")
+                self.last_log = {"step": step, "mean_value": mean_value, "norm": norm, "reward": reward,
+                                 "loss": loss, "mean_weight": mean_w, "time_per_step": dt}
+                print(f"step:{step} // mean_value:{mean_value:.3f} // norm: {norm:.3f} // REWARD:{reward:.3f} // "
+                      f"NUM_MEMORY:{len(self.memory.memory)} // Mean_Weight:{mean_w:.3f} // "
+                      f"MAX_WEIGHT:{self.memory.memory.max_weight:.3f} // TIME:{dt:.5f} // loss:{loss:.5f}")
                 if self.writer is not None:
+                    if n_rew:
+                        self.writer.add_scalar("Reward", reward, step)
                     self.writer.add_scalar("value", mean_value, step)
+                    self.writer.add_scalar("norm", norm, step)
+                if ckpt is not None:
+                    ckpt.snapshot(step)
                 acc, t0 = None, time.time()
         return step

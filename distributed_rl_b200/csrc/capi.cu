@@ -32,6 +32,7 @@ static void free_all(b2rl_replay* h) {
   if (h->mark) cudaFree(h->mark);
   if (h->scratch_val) cudaFree(h->scratch_val);
   if (h->rng_dev) cudaFree(h->rng_dev);
+  if (h->n_valid_dev) cudaFree(h->n_valid_dev);
 }
 
 extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) {
@@ -65,6 +66,7 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
   alloc((void**)&h->mark, sizeof(int32_t) * (size_t)h->cap2);
   alloc((void**)&h->scratch_val, sizeof(float) * (size_t)h->capacity);
   alloc((void**)&h->rng_dev, sizeof(uint64_t) * 3);   // {seed, counter, last-block ticket}
+  alloc((void**)&h->n_valid_dev, sizeof(float));
   if (e != cudaSuccess) {
     set_error("cudaMalloc failed while creating a %lld-slot replay: %s", (long long)d->capacity,
               cudaGetErrorString(e));

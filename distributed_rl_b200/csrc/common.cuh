@@ -123,6 +123,12 @@ __device__ __forceinline__ void st_node(TreeNode* p, double s, float m) {
   *reinterpret_cast<float4*>(p) = v;
 }
 
+struct b2rl_replay;
+namespace b2rl {
+// Stream-ordered publication of the host-side `size` to n_valid_dev (tree.cu).
+int publish_size(b2rl_replay* h, cudaStream_t st);
+}  // namespace b2rl
+
 // The opaque handle.
 struct b2rl_replay {
   int device = 0;
@@ -138,6 +144,8 @@ struct b2rl_replay {
   int64_t* scratch_idx = nullptr;  // [capacity] ring indices for push/evict
   float* scratch_val = nullptr;    // [capacity]
   uint64_t* rng_dev = nullptr;     // [3] device-resident Philox stream {seed, counter, ticket}
+  float* n_valid_dev = nullptr;    // [1] (float)size, rewritten in stream order whenever size changes: the
+                                   //     sampling / stats kernels read it, so a captured graph never bakes it in
   int64_t size = 0;       // valid slots
   int64_t head = 0;       // next slot to write
   int64_t reserved = 0;   // slots zeroed by b2rl_replay_reserve and not yet committed

@@ -282,7 +282,8 @@ k_fill_hash(uint8_t* __restrict__ base, int64_t row_bytes, int64_t n_rows, uint3
 using namespace b2rl;
 
 int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_start,
-                          const float* vals_dev, float const_val, int64_t n, cudaStream_t st);
+                          const float* vals_dev, float const_val, int64_t n, cudaStream_t st,
+                          bool publish_size_too);
 
 static int gather_chunk() {
   static int chunk = -1;
@@ -393,7 +394,7 @@ extern "C" int b2rl_replay_fill_hash(b2rl_replay* h, int64_t n, uint32_t seed, v
   B2RL_CHECK_LAUNCH();
   h->size = n;
   h->head = (n == h->capacity) ? 0 : n;
-  return B2RL_OK;
+  return publish_size(h, st);
 }
 
 extern "C" int b2rl_replay_push(b2rl_replay* h, const void* const* fields_src, const float* prios,
@@ -417,10 +418,10 @@ extern "C" int b2rl_replay_push(b2rl_replay* h, const void* const* fields_src, c
                                 cudaMemcpyDefault, st));
   }
   B2RL_CUDA(cudaMemcpyAsync(h->scratch_val, prios, (size_t)n * sizeof(float), cudaMemcpyDefault, st));
-  int rc = b2rl_tree_update_impl(h, nullptr, head, h->scratch_val, 0.0f, n, st);
+  h->size = (h->size + n > h->capacity) ? h->capacity : h->size + n;   // published by the update kernel itself
+  int rc = b2rl_tree_update_impl(h, nullptr, head, h->scratch_val, 0.0f, n, st, true);
   if (rc != B2RL_OK) return rc;
   h->head = (head + n) % h->capacity;
-  h->size = (h->size + n > h->capacity) ? h->capacity : h->size + n;
   return B2RL_OK;
 }
 
@@ -429,10 +430,10 @@ extern "C" int b2rl_replay_reserve(b2rl_replay* h, int64_t n, int64_t* start_slo
   B2RL_REQUIRE(n >= 1 && n <= h->capacity, "n out of range (1..capacity)");
   B2RL_REQUIRE(h->reserved == 0, "a reservation is already pending (call b2rl_replay_commit first)");
   DeviceGuard g(h->device);
-  int rc = b2rl_tree_update_impl(h, nullptr, h->head, nullptr, 0.0f, n, (cudaStream_t)stream);
-  if (rc != B2RL_OK) return rc;
-  const int64_t overwritten = h->size + n - h->capacity;     // records that just became unsampleable
+  const int64_t overwritten = h->size + n - h->capacity;     // records that become unsampleable now
   if (overwritten > 0) h->size -= overwritten;
+  int rc = b2rl_tree_update_impl(h, nullptr, h->head, nullptr, 0.0f, n, (cudaStream_t)stream, overwritten > 0);
+  if (rc != B2RL_OK) return rc;
   h->reserved = n;
   if (start_slot) *start_slot = h->head;
   return B2RL_OK;
@@ -462,10 +463,10 @@ extern "C" int b2rl_replay_commit(b2rl_replay* h, const float* prios, int64_t n,
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   B2RL_CUDA(cudaMemcpyAsync(h->scratch_val, prios, (size_t)n * sizeof(float), cudaMemcpyDefault, st));
-  int rc = b2rl_tree_update_impl(h, nullptr, h->head, h->scratch_val, 0.0f, n, st);
+  h->size = (h->size + n > h->capacity) ? h->capacity : h->size + n;
+  int rc = b2rl_tree_update_impl(h, nullptr, h->head, h->scratch_val, 0.0f, n, st, true);
   if (rc != B2RL_OK) return rc;
   h->head = (h->head + n) % h->capacity;
-  h->size = (h->size + n > h->capacity) ? h->capacity : h->size + n;
   h->reserved = 0;
   return B2RL_OK;
 }
@@ -478,8 +479,6 @@ extern "C" int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream) {
   // oldest record lives at (head - size) mod capacity
   int64_t tail = h->head - h->size;
   if (tail < 0) tail += h->capacity;
-  int rc = b2rl_tree_update_impl(h, nullptr, tail, nullptr, 0.0f, delta, (cudaStream_t)stream);
-  if (rc != B2RL_OK) return rc;
   h->size -= delta;
-  return B2RL_OK;
+  return b2rl_tree_update_impl(h, nullptr, tail, nullptr, 0.0f, delta, (cudaStream_t)stream, true);
 }

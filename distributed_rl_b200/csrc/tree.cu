@@ -88,7 +88,7 @@ constexpr int SAMPLE_THREADS = 128;
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 k_tree_sample(const TreeNode* __restrict__ node, int64_t cap2,
               int levels, const double* __restrict__ u01, uint64_t seed, uint64_t rng_offset,
-              const uint64_t* __restrict__ rng_state, int64_t n, float n_valid, float beta,
+              const uint64_t* __restrict__ rng_state, int64_t n, const float* __restrict__ n_valid_dev, float beta,
               const float* __restrict__ max_w_ext, int64_t* __restrict__ idx_out,
               float* __restrict__ prob_out, float* __restrict__ w_out) {
   const int64_t k = (int64_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x;
@@ -130,6 +130,7 @@ k_tree_sample(const TreeNode* __restrict__ node, int64_t cap2,
   const float prob = __fdiv_rn(p, s32);
   if (prob_out) prob_out[k] = prob;
   if (w_out) {
+    const float n_valid = *n_valid_dev;   // current number of valid slots (stream-ordered, not a launch constant)
     const float w_un = powcr(__fdiv_rn(1.0f, __fmul_rn(n_valid, prob)), beta);
     float max_w;
     if (max_w_ext) {
@@ -151,8 +152,11 @@ __global__ void k_philox_uniforms(uint64_t seed, uint64_t off, int64_t n, double
   if (k < n) out[k] = philox_u01(seed, off + (uint64_t)k);
 }
 
-__global__ void k_tree_stats(const TreeNode* __restrict__ node, float n_valid, float beta,
+__global__ void k_set_n_valid(float* __restrict__ n_valid_dev, float v) { *n_valid_dev = v; }
+
+__global__ void k_tree_stats(const TreeNode* __restrict__ node, const float* __restrict__ n_valid_dev, float beta,
                              double* __restrict__ out, float* __restrict__ max_w_out) {
+  const float n_valid = *n_valid_dev;
   const TreeNode r = ld_node(node + 1);
   const double root = r.s;
   const float s32 = (float)root;
@@ -262,8 +266,9 @@ constexpr int US_MAX_LEVELS = 24;
 __global__ void __launch_bounds__(US_THREADS, 1)
 k_update_sorted(const int64_t* __restrict__ idx, int64_t ring_start, int64_t capacity,
                 const float* __restrict__ vals, float const_val, int n, TreeNode* __restrict__ tree,
-                int64_t cap2, int levels) {
+                int64_t cap2, int levels, float* __restrict__ n_valid_dev, float n_valid_new) {
   __shared__ uint64_t s_key[US_THREADS];
+  if (n_valid_dev != nullptr && threadIdx.x == 0) *n_valid_dev = n_valid_new;   // ring size after this ingest step
   __shared__ uint32_t s_leaf[US_THREADS];
   __shared__ float s_valf[US_THREADS];
   __shared__ double s_sum[US_THREADS];
@@ -368,11 +373,19 @@ using namespace b2rl;
 
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+int b2rl::publish_size(b2rl_replay* h, cudaStream_t st) {
+  k_set_n_valid<<<1, 1, 0, st>>>(h->n_valid_dev, (float)h->size);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
 // idx_dev == nullptr means the ring range [ring_start, ring_start+n) (mod capacity);
 // vals_dev == nullptr means the constant `const_val`.
 int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_start,
-                          const float* vals_dev, float const_val, int64_t n, cudaStream_t st) {
-  if (n == 0) return B2RL_OK;
+                          const float* vals_dev, float const_val, int64_t n, cudaStream_t st,
+                          bool publish_size_too) {
+  if (n == 0) return publish_size_too ? publish_size(h, st) : B2RL_OK;
   static int force_atomic = -1;
   if (force_atomic < 0) {
     const char* e = getenv("B2RL_UPDATE");
@@ -382,10 +395,13 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
     // chunks are applied in stream order, so last-writer-wins also holds across chunks
     for (int64_t off = 0; off < n; off += US_THREADS) {
       const int m = (int)((n - off < US_THREADS) ? (n - off) : US_THREADS);
+      const bool last = off + US_THREADS >= n;
       k_update_sorted<<<1, US_THREADS, 0, st>>>(idx_dev ? idx_dev + off : nullptr,
                                                 (ring_start + off) % h->capacity, h->capacity,
                                                 vals_dev ? vals_dev + off : nullptr, const_val, m, h->node,
-                                                h->cap2, h->levels);
+                                                h->cap2, h->levels,
+                                                (publish_size_too && last) ? h->n_valid_dev : nullptr,
+                                                (float)h->size);
       count_launch();
     }
     B2RL_CHECK_LAUNCH();
@@ -399,7 +415,7 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
                                             h->mark, h->cap2, h->levels);
   count_launch(3);
   B2RL_CHECK_LAUNCH();
-  return B2RL_OK;
+  return publish_size_too ? publish_size(h, st) : B2RL_OK;
 }
 
 extern "C" int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n, void* stream) {
@@ -418,7 +434,7 @@ extern "C" int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n
   B2RL_CHECK_LAUNCH();
   h->size = n;
   h->head = (n == h->capacity) ? 0 : n;
-  return B2RL_OK;
+  return publish_size(h, st);
 }
 
 extern "C" int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t seed,
@@ -432,7 +448,7 @@ extern "C" int b2rl_tree_sample(b2rl_replay* h, const double* u01_dev, uint64_t 
   if (n == 0) return B2RL_OK;
   DeviceGuard g(h->device);
   k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(
-      h->node, h->cap2, h->levels, u01_dev, seed, rng_offset, nullptr, n, (float)h->size, beta,
+      h->node, h->cap2, h->levels, u01_dev, seed, rng_offset, nullptr, n, h->n_valid_dev, beta,
       max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
@@ -459,7 +475,7 @@ extern "C" int b2rl_tree_sample_stream(b2rl_replay* h, int64_t n, float beta, co
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   k_tree_sample<<<grid_for(n, SAMPLE_THREADS), SAMPLE_THREADS, 0, st>>>(
-      h->node, h->cap2, h->levels, nullptr, 0, 0, h->rng_dev, n, (float)h->size, beta,
+      h->node, h->cap2, h->levels, nullptr, 0, 0, h->rng_dev, n, h->n_valid_dev, beta,
       max_w_dev, idx_out_dev, prob_out_dev, w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();
@@ -483,14 +499,14 @@ extern "C" int b2rl_tree_update(b2rl_replay* h, const int64_t* idx_dev, const fl
   B2RL_REQUIRE(n == 0 || (idx_dev && vals_dev), "null idx/vals");
   B2RL_REQUIRE(n < (int64_t)0xFFFFFFFFLL, "batch too large");
   DeviceGuard g(h->device);
-  return b2rl_tree_update_impl(h, idx_dev, 0, vals_dev, 0.0f, n, (cudaStream_t)stream);
+  return b2rl_tree_update_impl(h, idx_dev, 0, vals_dev, 0.0f, n, (cudaStream_t)stream, false);
 }
 
 extern "C" int b2rl_tree_stats(b2rl_replay* h, float beta, double* stats_out_dev, float* max_w_out_dev,
                                void* stream) {
   B2RL_REQUIRE(h != nullptr && (stats_out_dev != nullptr || max_w_out_dev != nullptr), "null argument");
   DeviceGuard g(h->device);
-  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->node, (float)h->size, beta, stats_out_dev,
+  k_tree_stats<<<1, 1, 0, (cudaStream_t)stream>>>(h->node, h->n_valid_dev, beta, stats_out_dev,
                                                   max_w_out_dev);
   count_launch();
   B2RL_CHECK_LAUNCH();

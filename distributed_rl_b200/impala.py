@@ -41,6 +41,7 @@ class ImpalaConfig:
     BUFFER_SIZE: int = 9999
     LEARNER_DEVICE: str = "cuda:0"
     REDIS_SERVER: str = "localhost"
+    LOG_W: str | None = None
     OPTIM_INFO: dict = field(default_factory=lambda: {"name": "rmsprop", "lr": 6e-4, "decay": 0})
     MODEL: dict = field(default_factory=default_impala_model)
     FUSED_CONV1: bool = True     # conv_1 (4 -> 16 channels) of every frame through libb2rl's tcgen05 kernel
@@ -50,7 +51,7 @@ class ImpalaConfig:
         import configuration as C
         names = ("BATCHSIZE", "ACTION_SIZE", "GAMMA", "C_LAMBDA", "C_VALUE", "P_VALUE", "ENTROPY_R", "UNROLL_STEP",
                  "REPLAY_MEMORY_LEN", "BUFFER_SIZE", "LEARNER_DEVICE", "REDIS_SERVER", "OPTIM_INFO", "MODEL")
-        return ImpalaConfig(**{k: getattr(C, k) for k in names})
+        return ImpalaConfig(LOG_W=getattr(C, "LOG_W", None), **{k: getattr(C, k) for k in names})
 
 
 class Replay(threading.Thread):
@@ -63,16 +64,50 @@ class Replay(threading.Thread):
         self.store = R.DeviceReplay(self.cfg.REPLAY_MEMORY_LEN, R.impala_fields(self.cfg.UNROLL_STEP), self.device)
         self.deque = []
         self._connect = connect
+        self._lock = threading.Lock()
+        self._stop_evt = threading.Event()
+        self._rng = torch.Generator(device=self.device)        # uniform sampling stream (random.sample in the reference)
+        self._rng.manual_seed(0x1A9A1A)
 
     def push_arrays(self, s, a, mu, r, done):
         n = torch.as_tensor(done).numel()
-        self.store.push([s, a, mu, r, done], torch.ones(n))     # uniform replay: unit priorities
+        with self._lock:
+            self.store.push([s, a, mu, r, done], torch.ones(n))     # uniform replay: unit priorities
+
+    def push_records(self, blobs) -> None:
+        """ReplayMemory.push (baseline/utils.py:305-309) for the actors' pickled rollouts
+        (IMPALA/Player.py:183-190): FIFO ring, oldest rollouts overwritten beyond REPLAY_MEMORY_LEN."""
+        if not blobs:
+            return
+        import pickle
+        from .wire import decode_impala
+        self.push_arrays(*decode_impala([pickle.loads(b) for b in blobs], self.cfg.UNROLL_STEP))
+
+    def stop(self) -> None:
+        self._stop_evt.set()
+
+    def run(self):
+        """IMPALA/ReplayMemory.py:56-76: drain `trajectory`, push.  Batches are assembled on demand."""
+        if self._connect is None:
+            return
+        import time
+        from .wire import drain
+        while not self._stop_evt.is_set():
+            data = drain(self._connect, "trajectory")
+            if data:
+                self.push_records(data)
+            else:
+                time.sleep(0.002)
 
     def bufferSave(self, m: int = 1):
         """IMPALA/ReplayMemory.py:30-54 with random.sample's no-replacement semantics."""
-        B, size = self.cfg.BATCHSIZE, len(self.store)
-        idx = torch.randperm(size, device=self.device)[:B * m]
-        b = self.store.gather(idx)
+        B = self.cfg.BATCHSIZE
+        with self._lock:
+            size = len(self.store)
+            if B * m > size:
+                raise ValueError("Sample larger than population")      # what random.sample raises
+            idx = torch.randperm(size, device=self.device, generator=self._rng)[:B * m]
+            b = self.store.gather(idx)
         for k in range(m):
             sl = slice(k * B, (k + 1) * B)
             self.deque.append((b["state"][sl].transpose(0, 1).contiguous(), b["action"][sl].t().contiguous(),
@@ -90,13 +125,15 @@ class Replay(threading.Thread):
 
 
 class Learner:
-    def __init__(self, cfg: ImpalaConfig | None = None, connect=None):
+    def __init__(self, cfg: ImpalaConfig | None = None, connect=None, start_replay: bool = True):
         self.cfg = cfg or ImpalaConfig.from_configuration()
         self.device = torch.device(self.cfg.LEARNER_DEVICE)
         self.model = GraphAgent(self.cfg.MODEL).to(self.device)
         self.mOptim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
         self._connect = connect
         self._memory = Replay(self.cfg, connect)
+        if connect is not None and start_replay:
+            self._memory.start()                                # IMPALA/Learner.py:27-28
         self.last = {}
 
     def forward(self, state, action):
@@ -164,9 +201,20 @@ class Learner:
         return ({k: v.cpu() for k, v in self.model.state_dict().items()},)
 
     def run(self, max_steps=None):
+        """IMPALA/Learner.py:274-297: per step sample -> train, publish `params` (the 1-tuple of the state dict)
+        and `Count` EVERY step (:286-287), checkpoint every 100 steps (:290-297).  Publication is asynchronous:
+        the weights are snapshot on the learner stream and SET once their D2H copy has landed; if the previous
+        snapshot is still in flight this step's is skipped (the actors poll every 400 env steps anyway)."""
         import time
+        from . import wire
+        from .publish import ParamPublisher
         while len(self._memory) <= self.cfg.BUFFER_SIZE:
             time.sleep(0.05)
+        pub = ParamPublisher(self.model, self._connect, "params", "Count", wrap=lambda sd: (sd,))
+        ckpt_path = wire.checkpoint_path(self.cfg.LOG_W)
+        ckpt = ParamPublisher(self.model, None, None, None,
+                              on_ready=lambda sd, step: torch.save(sd, ckpt_path)) if ckpt_path else None
+        self._publishers = (pub,) + ((ckpt,) if ckpt else ())
         t = 0
         while max_steps is None or t < max_steps:
             tr = self._memory.sample()
@@ -174,5 +222,10 @@ class Learner:
                 time.sleep(0.2)
                 continue
             self.train(tr, t)
+            pub.snapshot(t)
+            if ckpt is not None and (t + 1) % 100 == 0:
+                ckpt.snapshot(t)
+            for p in self._publishers:
+                p.poll()
             t += 1
         return t

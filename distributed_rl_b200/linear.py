@@ -4,7 +4,7 @@ The reference's dense heads are `nn.Linear(..., bias=False)` (baseline/baseNetwo
 GPU PyTorch runs them as fp32 SIMT GEMMs.  `linear3x(x, w)` computes the same `x @ w.T` — forward,
 input gradient and weight gradient — with every operand split into two TF32 terms and three
 tcgen05 products per term pair, fp32 accumulation in TMEM (error ~2^-22 relative per product,
-the same order as an fp32 FMA chain; tests/test_gpu_gemm.py pins it against fp64).
+the same order as an fp32 FMA chain; tests/test_gpu_03_gemm.py pins it against fp64).
 """
 from __future__ import annotations
 

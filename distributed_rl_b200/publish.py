@@ -17,8 +17,12 @@ import torch
 
 
 class ParamPublisher:
-    def __init__(self, model: torch.nn.Module, connect, key: str = "state_dict", count_key: str | None = "count"):
+    def __init__(self, model: torch.nn.Module, connect, key: str | None = "state_dict",
+                 count_key: str | None = "count", wrap=None, on_ready=None):
+        """`wrap(sd)`: payload put under `key` (IMPALA publishes the 1-tuple `(sd,)`, IMPALA/Learner.py:268-272);
+        `on_ready(sd, step)`: extra consumer of a landed snapshot (e.g. the checkpoint writer)."""
         self.model, self.connect, self.key, self.count_key = model, connect, key, count_key
+        self.wrap, self.on_ready = wrap, on_ready
         sd = model.state_dict()
         self.names = list(sd.keys())
         self.shapes = [tuple(v.shape) for v in sd.values()]
@@ -62,10 +66,12 @@ class ParamPublisher:
             return False
         parts = torch.split(self.flat_host[slot], self.numels)
         sd = {k: p.view(s).clone() for k, p, s in zip(self.names, parts, self.shapes)}
-        if self.connect is not None:
-            self.connect.set(self.key, pickle.dumps(sd))
+        if self.connect is not None and self.key:
+            self.connect.set(self.key, pickle.dumps(self.wrap(sd) if self.wrap else sd))
             if self.count_key:
                 self.connect.set(self.count_key, pickle.dumps(step))
+        if self.on_ready is not None:
+            self.on_ready(sd, step)
         self.last = sd
         self.pending = None
         self.published += 1

@@ -56,6 +56,7 @@ class R2D2Config:
     TARGET_FREQUENCY: int = 2500
     LEARNER_DEVICE: str = "cuda:0"
     REDIS_SERVER: str = "localhost"
+    LOG_W: str | None = None
     OPTIM_INFO: dict = field(default_factory=lambda: {"name": "adam", "lr": 1e-4, "eps": 0.001})
     MODEL: dict = field(default_factory=default_r2d2_model)
     FUSED_CONV1: bool = True     # conv_1 of every frame through libb2rl's tcgen05 kernel (gather fused)
@@ -67,7 +68,7 @@ class R2D2Config:
         names = ("BATCHSIZE", "ACTION_SIZE", "ALPHA", "BETA", "GAMMA", "UNROLL_STEP", "FIXED_TRAJECTORY", "MEM",
                  "USE_RESCALING", "REPLAY_MEMORY_LEN", "BUFFER_SIZE", "TARGET_FREQUENCY", "LEARNER_DEVICE",
                  "REDIS_SERVER", "OPTIM_INFO", "MODEL")
-        return R2D2Config(**{k: getattr(C, k) for k in names})
+        return R2D2Config(LOG_W=getattr(C, "LOG_W", None), **{k: getattr(C, k) for k in names})
 
 
 class Replay(threading.Thread):
@@ -82,15 +83,57 @@ class Replay(threading.Thread):
         self.memory = _MemoryView(self.store, self.cfg.BETA)
         self.connect, self.cond, self.lock = connect, False, False
         self.deque, self.total_frame = [], 0
+        self._lock = threading.Lock()       # the reference's update() is unlocked (:48-51); the handle needs it
+        self._stop_evt = threading.Event()
 
     def push_arrays(self, s, a, r, h0, h1, notdone, p):
-        self.store.push([s, a, r, h0, h1, notdone], p)
+        with self._lock:
+            self.store.push([s, a, r, h0, h1, notdone], p)
         self.total_frame += int(torch.as_tensor(p).numel())
+
+    def push_records(self, blobs) -> None:
+        """PER.push for the actors' pickled sequences (R2D2/Player.py:312-319): decoded once on the host with
+        the indexing of R2D2/ReplayMemory.py:70-88, one batched H2D copy + leaf writes."""
+        if not blobs:
+            return
+        import pickle
+        from .wire import decode_r2d2
+        cols, p = decode_r2d2([pickle.loads(b) for b in blobs], self.cfg.FIXED_TRAJECTORY)
+        self.push_arrays(*cols, p)
+
+    def stop(self) -> None:
+        self._stop_evt.set()
+
+    def run(self):
+        """R2D2/ReplayMemory.py:141-178: drain `experience`, push, serve the eviction request."""
+        if self.connect is None:
+            return
+        import time
+        from .wire import drain
+        while not self._stop_evt.is_set():
+            data = drain(self.connect, "experience")
+            if data:
+                self.push_records(data)
+                self.cond = len(self.store) > self.cfg.BUFFER_SIZE
+            if self.lock:
+                self._evict_on_request()
+            if not data:
+                time.sleep(0.002)
+
+    def _evict_on_request(self) -> None:
+        if len(self.store) >= self.cfg.REPLAY_MEMORY_LEN:       # :165-173
+            with self._lock:
+                self.deque.clear()
+                over = len(self.store) - self.cfg.REPLAY_MEMORY_LEN
+                if over > 0:
+                    self.store.evict(over)
+        self.lock = False
 
     def buffer(self, m: int = 1):
         B = self.cfg.BATCHSIZE
-        idx, _, w = self.store.sample(B * m, beta=self.cfg.BETA)
-        b = self.store.gather(idx)
+        with self._lock:
+            idx, _, w = self.store.sample(B * m, beta=self.cfg.BETA)
+            b = self.store.gather(idx)
         for k in range(m):
             sl = slice(k * B, (k + 1) * B)
             h0 = b["h0"][sl].unsqueeze(0).contiguous()     # (1, B, 512) like torch.cat(..., 1) at :87-88
@@ -108,11 +151,12 @@ class Replay(threading.Thread):
     def update(self, idx, vals):
         if isinstance(idx, (list, tuple)):
             idx = torch.stack([torch.as_tensor(i) for i in idx])
-        self.store.update(torch.as_tensor(idx).to(self.device), torch.as_tensor(vals).to(self.device))
+        with self._lock:
+            self.store.update(torch.as_tensor(idx).to(self.device), torch.as_tensor(vals).to(self.device))
 
 
 class Learner:
-    def __init__(self, cfg: R2D2Config | None = None, connect=None):
+    def __init__(self, cfg: R2D2Config | None = None, connect=None, start_replay: bool = True, writer=None):
         self.cfg = cfg or R2D2Config.from_configuration()
         self.device = torch.device(self.cfg.LEARNER_DEVICE)
         self.model = GraphAgent(self.cfg.MODEL).to(self.device)
@@ -122,6 +166,12 @@ class Learner:
         self.optim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
         self.connect = connect
         self.memory = Replay(self.cfg, connect)
+        self.writer = writer
+        if connect is not None:
+            if start_replay:
+                self.memory.start()                              # R2D2/Learner.py:46-48
+            from .wire import wipe_stale_keys
+            wipe_stale_keys(connect)                             # :54,63-64
 
     def train(self, transition, t=0):
         c = self.cfg
@@ -215,19 +265,67 @@ class Learner:
     def target_state_dict(self):
         return {k: v.cpu() for k, v in self.target_model.state_dict().items()}
 
-    def run(self, max_steps=None):
+    def run(self, max_steps=None, log_every: int = 500):
+        """R2D2/Learner.py:217-339: wait for BUFFER_SIZE sequences, announce `Start`, then per step sample ->
+        train -> priority write-back; hard target sync every TARGET_FREQUENCY steps (+ `target_state_dict`),
+        `state_dict` / `count` (= step - 50, sic :293) every 25 steps, and every 500 steps the eviction request,
+        the `reward` drain + log line and a checkpoint.  Publication is asynchronous (ParamPublisher)."""
+        import pickle
         import time
+        from . import wire
+        from .publish import ParamPublisher
         while len(self.memory.memory) <= self.cfg.BUFFER_SIZE:
             time.sleep(0.05)
-        step = 0
+        if self.connect is not None:                                     # :227-234
+            self.connect.set("state_dict", pickle.dumps(self.state_dict))
+            self.connect.set("count", pickle.dumps(1))
+            self.connect.set("target_state_dict", pickle.dumps(self.target_state_dict))
+            self.connect.set("Start", pickle.dumps(True))
+        pub = ParamPublisher(self.model, self.connect, "state_dict", "count")
+        pub_t = ParamPublisher(self.target_model, self.connect, "target_state_dict", None)
+        ckpt_path = wire.checkpoint_path(self.cfg.LOG_W)
+        ckpt = ParamPublisher(self.model, None, None, None,
+                              on_ready=lambda sd, step: torch.save(sd, ckpt_path)) if ckpt_path else None
+        self._publishers = (pub, pub_t) + ((ckpt,) if ckpt else ())
+        step, acc, t0 = 0, None, time.time()
+        self.last_log = None
         while max_steps is None or step < max_steps:
             batch = self.memory.sample()
             if batch is False:
                 time.sleep(0.002)
                 continue
             info, prio, idx = self.train(batch)
-            self.memory.update(idx, prio)
             step += 1
-            if step % self.cfg.TARGET_FREQUENCY == 0:
+            if step % log_every == 0:
+                self.memory.lock = True                                  # :266-268
+                if self.connect is None or not self.memory.is_alive():
+                    self.memory._evict_on_request()
+            if not self.memory.lock:
+                self.memory.update(idx, prio)                            # :271-274
+            tot = torch.stack([info["mean_value"].reshape(()), info["p_norm"].reshape(())])
+            acc = tot if acc is None else acc + tot
+            if step % self.cfg.TARGET_FREQUENCY == 0:                    # :283-286
                 self.target_model.updateParameter(self.model, 1)
+                pub_t.snapshot(step)
+            if step % 25 == 0:                                           # :288-293
+                pub.snapshot(step - 50)
+            for p in self._publishers:
+                p.poll()
+            if step % log_every == 0:                                    # :296-339
+                reward, n_rew = wire.drain_rewards(self.connect) if self.connect is not None else (-21.0, 0)
+                mean_value, norm = (acc / log_every).tolist()
+                dt = (time.time() - t0) / log_every
+                self.last_log = {"step": step, "mean_value": mean_value, "norm": norm, "reward": reward,
+                                 "time_per_step": dt}
+                print(f"step:{step} // mean_value:{mean_value:.3f} // norm: {norm:.3f} // REWARD:{reward:.3f} // "
+                      f"NUM_MEMORY:{len(self.memory.memory)} // MAX_WEIGHT:{self.memory.memory.max_weight:.3f} // "
+                      f"TIME:{dt:.5f}")
+                if self.writer is not None:
+                    if n_rew:
+                        self.writer.add_scalar("Reward", reward, step)
+                    self.writer.add_scalar("value", mean_value, step)
+                    self.writer.add_scalar("norm", norm, step)
+                if ckpt is not None:
+                    ckpt.snapshot(step)
+                acc, t0 = None, time.time()
         return step
