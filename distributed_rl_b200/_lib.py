@@ -35,6 +35,7 @@ SIGNATURES = {
     "b2rl_tree_sample": (C.c_int, [c_vp, c_vp, c_u64, c_u64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2rl_replay_seed": (C.c_int, [c_vp, c_u64, c_u64, c_vp]),
     "b2rl_tree_sample_stream": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2rl_tree_sample_fetch": (C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_vp), c_vp]),
     "b2rl_philox_uniforms": (C.c_int, [c_u64, c_u64, c_i64, c_vp, c_vp]),
     "b2rl_tree_update": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "b2rl_tree_stats": (C.c_int, [c_vp, c_f32, c_vp, c_vp, c_vp]),

@@ -545,14 +545,24 @@ class Learner:
                 max_w = self._max_w_use
             side = fused_conv1 and self.cfg.PARALLEL_FORWARDS
             packs_done = self._pack_conv1_async() if side else None
-            idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
             if fused_conv1:
-                if not hasattr(self, "_small"):
-                    self._small = st.alloc_batch(B, ("action", "reward", "done"))
-                b = st.gather(idx, self._small)        # scalar fields only; frames go through conv1_fused
-                out = self._forward_backward_fused(idx, b["action"].to(torch.int64), b["reward"], b["done"], w,
+                # ONE launch draws the minibatch: indices + IS weights from the sum-tree and the sampled slots'
+                # scalar fields (a, r, done); the frames are read in place by the conv_1 kernels.
+                # (Drawing the NEXT minibatch at the end of the step would hide these ~5 us too, but a ring slot
+                # overwritten by the ingest between the draw and its use would pair new frames with the old
+                # record's a / r / done — DESIGN.md §4.2.)
+                if not hasattr(self, "_cur"):
+                    self._cur = dict(st.alloc_batch(B, ("action", "reward", "done")),
+                                     idx=torch.empty(B, dtype=torch.int64, device=self.device),
+                                     w=torch.empty(B, dtype=torch.float32, device=self.device))
+                c = self._cur
+                st.sample_fetch(B, self.cfg.BETA, c["idx"], c["w"], {k: c[k] for k in ("action", "reward", "done")},
+                                max_w=max_w)
+                idx = c["idx"]
+                out = self._forward_backward_fused(idx, c["action"].to(torch.int64), c["reward"], c["done"], c["w"],
                                                    packs_done=packs_done, update_tree=side)
             else:
+                idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
                 b = st.gather(idx)
                 out = self._forward_backward(b["state"], b["action"].to(torch.int64), b["reward"],
                                              b["next_state"], b["done"], w)

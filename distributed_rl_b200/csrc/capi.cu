@@ -27,12 +27,14 @@ extern "C" int64_t b2rl_launch_count(void) { return g_launches.load(std::memory_
 static void free_all(b2rl_replay* h) {
   for (int f = 0; f < B2RL_MAX_FIELDS; ++f)
     if (h->field[f]) cudaFree(h->field[f]);
-  if (h->node) cudaFree(h->node);
+  if (h->tree.leaf) cudaFree(h->tree.leaf);
+  if (h->tree.sum) cudaFree(h->tree.sum);
+  if (h->tree.minv) cudaFree(h->tree.minv);
   if (h->tag) cudaFree(h->tag);
-  if (h->mark) cudaFree(h->mark);
   if (h->scratch_val) cudaFree(h->scratch_val);
   if (h->rng_dev) cudaFree(h->rng_dev);
   if (h->n_valid_dev) cudaFree(h->n_valid_dev);
+  if (h->build_ticket) cudaFree(h->build_ticket);
 }
 
 extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) {
@@ -48,9 +50,20 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
   if (!h) { set_error("out of host memory"); return B2RL_ERR_NOMEM; }
   h->device = d->device;
   h->capacity = d->capacity;
-  h->levels = 0;
-  h->cap2 = 1;
+  h->levels = 1;            // at least two leaves, so that there is always a stored root level above them
+  h->cap2 = 2;
   while (h->cap2 < d->capacity) { h->cap2 <<= 1; h->levels++; }
+  TreeView& t = h->tree;
+  t.cap2 = h->cap2;
+  t.levels = h->levels;
+  t.G = (h->levels + 3) / 4;
+  t.top_bits = h->levels - 4 * (t.G - 1);
+  int64_t total = 0;
+  for (int k = 1; k <= t.G; ++k) {
+    t.off[k] = total;
+    const int64_t nk = (k == t.G) ? 1 : (h->cap2 >> (4 * k));
+    total += (nk + 15) & ~(int64_t)15;     // every stored level starts on a 128-byte line
+  }
   h->n_fields = d->n_fields;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
@@ -61,12 +74,14 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
     // +16 B so a 16-byte bulk/vector access on the last row never leaves the allocation
     alloc((void**)&h->field[f], (size_t)d->capacity * (size_t)d->field_bytes[f] + 16);
   }
-  alloc((void**)&h->node, sizeof(TreeNode) * 2 * (size_t)h->cap2);
+  alloc((void**)&t.leaf, sizeof(float) * (size_t)h->cap2);
+  alloc((void**)&t.sum, sizeof(double) * (size_t)total);
+  alloc((void**)&t.minv, sizeof(float) * (size_t)total);
   alloc((void**)&h->tag, sizeof(uint32_t) * (size_t)h->cap2);
-  alloc((void**)&h->mark, sizeof(int32_t) * (size_t)h->cap2);
   alloc((void**)&h->scratch_val, sizeof(float) * (size_t)h->capacity);
   alloc((void**)&h->rng_dev, sizeof(uint64_t) * 3);   // {seed, counter, last-block ticket}
   alloc((void**)&h->n_valid_dev, sizeof(float));
+  alloc((void**)&h->build_ticket, sizeof(unsigned int));
   if (e != cudaSuccess) {
     set_error("cudaMalloc failed while creating a %lld-slot replay: %s", (long long)d->capacity,
               cudaGetErrorString(e));
@@ -75,13 +90,13 @@ extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) 
     cudaGetLastError();
     return B2RL_ERR_NOMEM;
   }
-  // empty tree: sums 0, mins +inf, tags/marks 0
+  B2RL_CUDA(cudaMemset(h->build_ticket, 0, sizeof(unsigned int)));
+  // empty tree: sums 0, mins +inf, tags 0
   {
     int rc = b2rl_tree_build(h, nullptr, 0, nullptr);   // empty tree: sums 0, mins +inf
     if (rc != B2RL_OK) { free_all(h); delete h; return rc; }
   }
   B2RL_CUDA(cudaMemset(h->tag, 0, sizeof(uint32_t) * (size_t)h->cap2));
-  B2RL_CUDA(cudaMemset(h->mark, 0, sizeof(int32_t) * (size_t)h->cap2));
   {
     const uint64_t init[3] = {1234ULL, 0ULL, 0ULL};
     B2RL_CUDA(cudaMemcpy(h->rng_dev, init, sizeof(init), cudaMemcpyHostToDevice));

@@ -97,31 +97,21 @@ __host__ __device__ __forceinline__ double philox_u01(uint64_t seed, uint64_t ct
 
 }  // namespace b2rl
 
-// One sum-tree node: subtree sum (fp64) and subtree min over valid (p > 0) leaves (fp32) in ONE
-// 16-byte record, so a path update or a descent touches one sector per node instead of two.
-struct __align__(16) TreeNode {
-  double s;
-  float m;
-  float pad;
+// The sum-tree as the kernels see it (tree.cu): a binary tree of depth `levels` stored sparsely — every 4th
+// level only.  Stored level 0 = leaves (fp32 priorities, 0 = empty slot); stored level k (1 <= k < G) = binary
+// depth levels-4k as fp64 sums + fp32 mins over valid leaves; stored level G = the root.  The levels in between
+// are recomputed in registers with the binary tree's own pairwise association (bit-identical values).
+constexpr int B2RL_TREE_MAX_GROUPS = 8;   // levels <= 32
+struct TreeView {
+  float* leaf;                              // [cap2]
+  double* sum;                              // stored level k at sum + off[k]
+  float* minv;                              // stored level k at minv + off[k]
+  int64_t off[B2RL_TREE_MAX_GROUPS + 1];    // off[0] unused
+  int64_t cap2;                             // leaves = 2^levels >= max(capacity, 2)
+  int levels;
+  int G;                                    // ceil(levels / 4) stored internal levels
+  int top_bits;                             // binary levels spanned by the top group: levels - 4(G-1), in 1..4
 };
-__device__ __forceinline__ TreeNode ld_node(const TreeNode* p) {
-  const float4 v = *reinterpret_cast<const float4*>(p);
-  TreeNode n;
-  memcpy(&n, &v, sizeof(n));
-  return n;
-}
-__device__ __forceinline__ TreeNode ld_node_cg(const TreeNode* p) {   // L2 only: node may be written by another SM
-  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
-  TreeNode n;
-  memcpy(&n, &v, sizeof(n));
-  return n;
-}
-__device__ __forceinline__ void st_node(TreeNode* p, double s, float m) {
-  TreeNode n{s, m, 0.0f};
-  float4 v;
-  memcpy(&v, &n, sizeof(n));
-  *reinterpret_cast<float4*>(p) = v;
-}
 
 struct b2rl_replay;
 namespace b2rl {
@@ -133,17 +123,17 @@ int publish_size(b2rl_replay* h, cudaStream_t st);
 struct b2rl_replay {
   int device = 0;
   int64_t capacity = 0;   // requested slots
-  int64_t cap2 = 0;       // tree leaves = 2^levels >= capacity
+  int64_t cap2 = 0;       // tree leaves = 2^levels >= max(capacity, 2)
   int levels = 0;
   int n_fields = 0;
   int64_t field_bytes[B2RL_MAX_FIELDS] = {0};
   uint8_t* field[B2RL_MAX_FIELDS] = {nullptr};
-  TreeNode* node = nullptr;   // [2*cap2] implicit heap, node 1 = root, leaf j = cap2 + j
-  uint32_t* tag = nullptr;    // [cap2]   last-writer tags, self-cleaning
-  int32_t* mark = nullptr;    // [cap2]   per-internal-node side bits + arrival count, self-cleaning
+  TreeView tree = {};         // leaves + sparse fp64 levels (owned: tree.leaf, tree.sum, tree.minv)
+  uint32_t* tag = nullptr;    // [cap2]   last-writer tags of the large scattered update, self-cleaning
   int64_t* scratch_idx = nullptr;  // [capacity] ring indices for push/evict
   float* scratch_val = nullptr;    // [capacity]
   uint64_t* rng_dev = nullptr;     // [3] device-resident Philox stream {seed, counter, ticket}
+  unsigned int* build_ticket = nullptr;   // [1] last-CTA-done counter of the bulk build, self re-arming
   float* n_valid_dev = nullptr;    // [1] (float)size, rewritten in stream order whenever size changes: the
                                    //     sampling / stats kernels read it, so a captured graph never bakes it in
   int64_t size = 0;       // valid slots

@@ -103,15 +103,23 @@ class Replay(threading.Thread):
         """IMPALA/ReplayMemory.py:30-54 with random.sample's no-replacement semantics."""
         B = self.cfg.BATCHSIZE
         with self._lock:
-            size = len(self.store)
-            if B * m > size:
-                raise ValueError("Sample larger than population")      # what random.sample raises
-            idx = torch.randperm(size, device=self.device, generator=self._rng)[:B * m]
+            idx = self.draw(B * m)
             b = self.store.gather(idx)
         for k in range(m):
             sl = slice(k * B, (k + 1) * B)
             self.deque.append((b["state"][sl].transpose(0, 1).contiguous(), b["action"][sl].t().contiguous(),
                                b["mu"][sl].t().contiguous(), b["reward"][sl].t().contiguous(), b["done"][sl]))
+
+    def draw(self, n: int) -> torch.Tensor:
+        """n distinct slots, uniformly (random.sample over the list of kept rollouts, baseline/utils.py:310-315).
+        The kept rollouts are the ring's valid region [head - size, head): slots reserved for an ingest in flight
+        are outside it and are never read while they are being overwritten."""
+        size, cap, head = self.store._sizes()
+        if n > size:
+            raise ValueError("Sample larger than population")      # what random.sample raises
+        k = torch.randperm(size, device=self.device, generator=self._rng)[:n]
+        tail = (head - size) % cap
+        return (k + tail) % cap if tail else k
 
     def sample(self):
         if not self.deque:
@@ -146,10 +154,43 @@ class Learner:
 
     def train(self, transition, step=0):
         c = self.cfg
-        T, B, A = c.UNROLL_STEP, c.BATCHSIZE, c.ACTION_SIZE
+        T, B = c.UNROLL_STEP, c.BATCHSIZE
         dev = self.device
         state, action, mu, reward, done = [torch.as_tensor(x).to(dev) for x in transition]
         fused = c.FUSED_CONV1 and state.dtype == torch.uint8 and self.model.first_conv_node() is not None
+        if fused:   # the staged batch is the frame table: rows already are time-major
+            frames = state.contiguous().view((T + 1) * B, 4, 84, 84)
+            self._train_core(frames, None, action, mu, reward, done, step)
+        else:
+            self._train_core(state, "staged", action, mu, reward, done, step)
+
+    def fused_step(self, step=0):
+        """One learner step with everything resident: draw B rollouts uniformly without replacement
+        (random.sample, baseline/utils.py:310-315), gather only a / mu / r / done (244 B of the 593 KB rollout),
+        run conv_1 over the rollouts' (T+1) frames IN PLACE in the replay payload (row = slot * (T+1) + t,
+        time-major), V-trace kernel, loss, backward, clip + RMSprop."""
+        c = self.cfg
+        T, B = c.UNROLL_STEP, c.BATCHSIZE
+        mem = self._memory
+        st = mem.store
+        if not hasattr(self, "_small"):
+            self._small = st.alloc_batch(B, ("action", "mu", "reward", "done"))
+            self._frames = st.field_view("state").view(-1, 4, 84, 84)
+            self._t_idx = torch.arange(T + 1, device=self.device).view(T + 1, 1)
+        idx = mem.draw(B)
+        b = st.gather(idx, self._small)
+        rows = (idx.view(1, B) * (T + 1) + self._t_idx).reshape(-1).contiguous()
+        self._train_core(self._frames, rows, b["action"].t().contiguous(), b["mu"].t().contiguous(),
+                         b["reward"].t().contiguous(), b["done"], step)
+        return self.last
+
+    def _train_core(self, frames, rows, action, mu, reward, done, step):
+        """IMPALA/Learner.py:121-235 on a uint8 frame table read in place (`rows`: time-major frame rows, None =
+        all rows in order) or, with rows == "staged", on a staged (T+1, B, 28224) batch through PyTorch's conv_1."""
+        c = self.cfg
+        T, B, A = c.UNROLL_STEP, c.BATCHSIZE, c.ACTION_SIZE
+        dev = self.device
+        fused = not isinstance(rows, str)
         with torch.no_grad():
             if fused:
                 # one launch: conv_1 of all (T+1)*B frame stacks, uint8 -> /255 folded in, no fp32 staging
@@ -158,13 +199,12 @@ class Learner:
                     self._pack1 = R.Conv1Pack(1, dev, getattr(self.model, self._conv_name).conv_1.out_channels)
                 w1 = getattr(self.model, self._conv_name).conv_1.weight
                 self._pack1.pack(0, w1)
-                frames = state.contiguous().view((T + 1) * B, 4, 84, 84)
-                y_all = R.conv1_fused(frames, None, self._pack1, relu=False)[0]
+                y_all = R.conv1_fused(frames, rows, self._pack1, relu=False)[0]
                 y_seq, y_last = y_all[:T * B], y_all[T * B:]
                 out_last = self.model.forward_from_conv1(y_last, False)[0]
                 out_seq = self.model.forward_from_conv1(y_seq, False)[0]
             else:
-                s = state.float().div_(255.0).view(T + 1, B, 4, 84, 84)        # :131-140
+                s = frames.float().div_(255.0).view(T + 1, B, 4, 84, 84)        # :131-140
                 last, seq = s[-1], s[:-1].reshape(-1, 4, 84, 84)
                 out_last = self.model.forward([last])[0]
                 out_seq = self.model.forward([seq])[0]
@@ -177,7 +217,9 @@ class Learner:
                                c.GAMMA, c.C_LAMBDA, c.C_VALUE, c.P_VALUE)       # :151-215 in one launch
         # calLoss (:95-119): second forward with grad (conv_1's output is reused: same weights, same frames)
         if fused:
-            y = _Conv1Gathered.apply(w1, frames[:T * B], None, self._pack1, torch.contiguous_format, None, y_seq)
+            seq_frames = frames[:T * B] if rows is None else frames
+            seq_rows = None if rows is None else rows[:T * B]
+            y = _Conv1Gathered.apply(w1, seq_frames, seq_rows, self._pack1, torch.contiguous_format, None, y_seq)
             out = self.model.forward_from_conv1(y, False)[0]
         else:
             out = self.model.forward([seq])[0]

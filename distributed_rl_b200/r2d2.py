@@ -59,6 +59,9 @@ class R2D2Config:
     LOG_W: str | None = None
     OPTIM_INFO: dict = field(default_factory=lambda: {"name": "adam", "lr": 1e-4, "eps": 0.001})
     MODEL: dict = field(default_factory=default_r2d2_model)
+    PAYLOAD_POOL: int = 0        # > 0: the sum-tree has REPLAY_MEMORY_LEN slots but only this many distinct sequences
+                                 #      are stored, slot s reading row s % PAYLOAD_POOL (2^20 x 2.26 MB = 2.4 TB
+                                 #      does not fit HBM).  Benchmark-only; ingest needs 0.
     FUSED_CONV1: bool = True     # conv_1 of every frame through libb2rl's tcgen05 kernel (gather fused)
     FUSED_HEADS: bool = True     # dueling heads: 3xTF32 tcgen05 GEMM + fused tail kernels (csrc/gemm.cu, csrc/dueling.cu)
 
@@ -78,8 +81,13 @@ class Replay(threading.Thread):
         super().__init__(daemon=True)
         self.cfg = cfg or R2D2Config.from_configuration()
         self.device = torch.device(self.cfg.LEARNER_DEVICE)
-        self.store = R.DeviceReplay(self.cfg.REPLAY_MEMORY_LEN, R.r2d2_fields(self.cfg.FIXED_TRAJECTORY),
-                                    self.device)
+        fields = R.r2d2_fields(self.cfg.FIXED_TRAJECTORY)
+        if self.cfg.PAYLOAD_POOL:
+            self.store = R.DeviceReplay(self.cfg.REPLAY_MEMORY_LEN, (), self.device)          # priorities only
+            self.pool = R.DeviceReplay(self.cfg.PAYLOAD_POOL, fields, self.device)           # the stored sequences
+        else:
+            self.store = R.DeviceReplay(self.cfg.REPLAY_MEMORY_LEN, fields, self.device)
+            self.pool = self.store
         self.memory = _MemoryView(self.store, self.cfg.BETA)
         self.connect, self.cond, self.lock = connect, False, False
         self.deque, self.total_frame = [], 0
@@ -133,13 +141,17 @@ class Replay(threading.Thread):
         B = self.cfg.BATCHSIZE
         with self._lock:
             idx, _, w = self.store.sample(B * m, beta=self.cfg.BETA)
-            b = self.store.gather(idx)
+            b = self.pool.gather(self.rows_of(idx))
         for k in range(m):
             sl = slice(k * B, (k + 1) * B)
             h0 = b["h0"][sl].unsqueeze(0).contiguous()     # (1, B, 512) like torch.cat(..., 1) at :87-88
             h1 = b["h1"][sl].unsqueeze(0).contiguous()
             self.deque.append([(h0, h1), b["state"][sl], b["action"][sl], b["reward"][sl], b["notdone"][sl],
                                w[sl], idx[sl]])
+
+    def rows_of(self, idx: torch.Tensor) -> torch.Tensor:
+        """payload row of each sampled slot (identity unless PAYLOAD_POOL)."""
+        return idx % self.cfg.PAYLOAD_POOL if self.cfg.PAYLOAD_POOL else idx
 
     def sample(self):
         if not self.deque:
@@ -186,7 +198,8 @@ class Learner:
         state = torch.as_tensor(state).to(dev)
         fused = c.FUSED_CONV1 and state.dtype == torch.uint8 and self.model.first_conv_node() is not None
         if fused:
-            q, q_target = self._forward_fused(state.contiguous(), T, MEM, B, A)
+            frames = state.contiguous().view(B * T, 4, 84, 84)
+            q, q_target = self._forward_fused(frames, self._time_major_rows(None, T, B), T, MEM, B, A)
         else:
             state = state.float() / 255.0                       # :89-90
             sv = state.permute(1, 0, 2, 3, 4).contiguous()      # time-major, :93
@@ -213,23 +226,30 @@ class Learner:
         info["loss"] = out["scalars"][0]
         return info, out["prio"], idx
 
-    def _forward_fused(self, state_u8, T, MEM, B, A):
-        """Same forward passes with conv_1 on the tensor cores: the (b, t) -> time-major reordering and
-        the uint8 -> /255 conversion are folded into the kernel's gather (row index = b*T + t)."""
+    def _time_major_rows(self, seq_rows, T, B):
+        """Frame-table rows of the (t, b) frames in time-major order: row = seq_row[b] * T + t
+        (seq_rows None: the batch itself is the table, sequence b = rows b*T ... b*T+T-1)."""
+        dev = self.device
+        if not hasattr(self, "_t_idx"):
+            self._t_idx = torch.arange(T, device=dev).view(T, 1)
+            self._b_idx = torch.arange(B, device=dev).view(1, B)
+        base = self._b_idx if seq_rows is None else seq_rows.view(1, B)
+        return (base * T + self._t_idx).reshape(-1).contiguous()
+
+    def _forward_fused(self, frames, tm_rows, T, MEM, B, A):
+        """The forward passes with conv_1 on the tensor cores, reading `frames` (a uint8 (rows, 4, 84, 84) table:
+        the staged batch or the replay payload itself) IN PLACE: the (b, t) -> time-major reordering and the
+        uint8 -> /255 conversion are folded into the kernel's gather (`tm_rows`)."""
         dev = self.device
         if not hasattr(self, "_pack2"):
             self._conv_name = self.model.first_conv_node()
             c_out = getattr(self.model, self._conv_name).conv_1.out_channels
             self._pack2 = R.Conv1Pack(2, dev, c_out)
             self._pack1 = R.Conv1Pack(1, dev, c_out)
-            t_idx = torch.arange(T, device=dev).view(T, 1)
-            b_idx = torch.arange(B, device=dev).view(1, B)
-            self._tm_rows = (b_idx * T + t_idx).reshape(-1).contiguous()      # time-major list of (b, t) rows
-        frames = state_u8.view(B * T, 4, 84, 84)
         w_on = getattr(self.model, self._conv_name).conv_1.weight
         w_tg = getattr(self.target_model, self._conv_name).conv_1.weight
         self._pack2.pack(0, w_on); self._pack2.pack(1, w_tg); self._pack1.pack(0, w_on)
-        rows_burn, rows_win = self._tm_rows[:MEM * B], self._tm_rows[MEM * B:]
+        rows_burn, rows_win = tm_rows[:MEM * B], tm_rows[MEM * B:]
         L = T - MEM
         with torch.no_grad():                                   # burn-in, :99-104
             y_on, y_tg = R.conv1_fused(frames, rows_burn, self._pack2, relu=True)
@@ -246,6 +266,34 @@ class Learner:
         with torch.no_grad():
             q_target = self.target_model.forward_from_conv1(torch.relu(y_tg_w), True, [shape])[0].view(L, B, A)
         return q, q_target
+
+    def fused_step(self):
+        """One learner step with everything resident: sample B sequence slots + IS weights from the sum-tree,
+        gather only the small per-sequence fields (a, r, h0, h1, notdone: 5 KB of the 2.26 MB), run conv_1 over the
+        sequences' frames IN PLACE in the replay payload (row = slot_row * T + t), target / priority kernel,
+        backward, clip + Adam, priority write-back.  No host round trip (R2D2/Learner.py:235-274 in one call)."""
+        c = self.cfg
+        T, MEM, B, A = c.FIXED_TRAJECTORY, c.MEM, c.BATCHSIZE, c.ACTION_SIZE
+        mem = self.memory
+        st, pool = mem.store, mem.pool
+        if not hasattr(self, "_small"):
+            self._small = pool.alloc_batch(B, ("action", "reward", "h0", "h1", "notdone"))
+            self._frames = pool.field_view("state").view(-1, 4, 84, 84)
+        idx, _, w = st.sample(B, beta=c.BETA, want_prob=False)
+        rows = mem.rows_of(idx)
+        b = pool.gather(rows, self._small)
+        h0, h1 = b["h0"].unsqueeze(0), b["h1"].unsqueeze(0)
+        self.model.setCellState((h0, h1))
+        self.target_model.setCellState((h0, h1))
+        q, q_target = self._forward_fused(self._frames, self._time_major_rows(rows, T, B), T, MEM, B, A)
+        act = b["action"].to(torch.int64).t()[MEM:-1].contiguous()
+        rew = b["reward"].t()[MEM:-1].contiguous()
+        out = R.r2d2_target(q.detach().contiguous(), q_target.contiguous(), act, rew, b["notdone"], w,
+                            c.UNROLL_STEP, c.GAMMA, c.ALPHA, c.USE_RESCALING)
+        q.backward(out["grad_q"])
+        info = self.step()
+        st.update(idx, out["prio"])
+        return {"scalars": out["scalars"], "p_norm": info["p_norm"], "prio": out["prio"], "idx": idx}
 
     def step(self):
         """R2D2/Learner.py:200-215: norm, clip at 40, Adam."""

@@ -252,6 +252,20 @@ class DeviceReplay:
                                                    w.data_ptr(), self._st()))
         return idx, prob, w
 
+    def sample_fetch(self, n: int, beta: float, idx: torch.Tensor, w: torch.Tensor, small: dict,
+                     max_w: torch.Tensor | None = None, prob: torch.Tensor | None = None):
+        """sample() from the device-resident Philox stream into the given buffers AND, in the same launch, copy
+        the sampled slots' scalar fields (1/2/4/8-byte rows, e.g. action / reward / done) into `small[name]`.
+        Everything is written in place, so a captured graph can prefetch the next minibatch's indices."""
+        ptrs = (C.c_void_p * _lib.MAX_FIELDS)()
+        for i, f in enumerate(self.fields):
+            t = small.get(f.name)
+            ptrs[i] = t.data_ptr() if t is not None else None
+        check(self.lib.b2rl_tree_sample_fetch(self._h, int(n), float(beta), max_w.data_ptr() if max_w is not None else None,
+                                              idx.data_ptr(), prob.data_ptr() if prob is not None else None,
+                                              w.data_ptr(), ptrs, self._st()))
+        return idx, prob, w
+
     def sample_counter(self, seed: int, counter: int, n: int, beta: float = 0.4):
         """Stateless Philox draw: uniform k = philox(seed, counter + k)."""
         idx = torch.empty(n, dtype=torch.int64, device=self.device)

@@ -135,6 +135,15 @@ int b2rl_replay_seed(b2rl_replay* h, uint64_t seed, uint64_t counter, void* stre
 int b2rl_tree_sample_stream(b2rl_replay* h, int64_t n, float beta, const float* max_w_dev,
                             int64_t* idx_out_dev, float* prob_out_dev, float* w_out_dev, void* stream);
 
+/* b2rl_tree_sample_stream + the part of Replay.buffer (APE_X/ReplayMemory.py:74-93) that unpacks the SCALAR
+ * fields of the sampled records (action, reward, done): for every field f with small_fields_out_dev[f] != NULL
+ * (field_bytes[f] must be 1, 2, 4 or 8) row idx[k] is copied to small_fields_out_dev[f] + k*field_bytes[f] by the
+ * sampling thread itself, so a learner step needs no separate gather launch for them (the frame fields are read
+ * in place by b2rl_conv1_fused).  small_fields_out_dev may be NULL (= b2rl_tree_sample_stream). */
+int b2rl_tree_sample_fetch(b2rl_replay* h, int64_t n, float beta, const float* max_w_dev,
+                           int64_t* idx_out_dev, float* prob_out_dev, float* w_out_dev,
+                           void* const* small_fields_out_dev, void* stream);
+
 /* The uniforms b2rl_tree_sample would draw for (seed, rng_offset) in place of torch.multinomial's generator
  * (baseline/PER.py:97) — lets a
  * test replay a device-RNG run through the oracle. */

@@ -1,6 +1,7 @@
 """numpy restatements of the exact-arithmetic tricks the tensor-core kernels rely on (no GPU):
 the claims in DESIGN.md §4.6 / §4.9 / §4.10 about what is exact are checked here bit for bit."""
 import numpy as np
+import pytest
 
 
 def test_balanced_base256_digits_via_bias_reconstruct_exactly():
@@ -73,3 +74,61 @@ def test_int32_accumulator_bound_of_the_wgrad_kernel():
     """MAX_ITEMS_PER_CTA = 160: |sum| <= 128 * 255 * 400 * 160 < 2^31 (digit x pixel x positions x items)."""
     assert 128 * 255 * 400 * 160 < 2 ** 31
     assert 128 * 255 * 400 * 165 >= 2 ** 31
+
+
+# --------------------------------------------------------------------------- #
+# csrc/tree.cu: the sparse (every-4th-level) sum-tree reproduces the binary tree bit for bit    #
+# --------------------------------------------------------------------------- #
+def _r16_model(p, levels):
+    """numpy restatement of csrc/tree.cu's layout: stored level 0 = fp32 leaves, stored level k = binary depth
+    levels-4k as fp64, each node = pairwise16 of its (zero-padded) 16 children."""
+    cap2 = 1 << levels
+    G = (levels + 3) // 4
+    top_bits = levels - 4 * (G - 1)
+    leaf = np.zeros(cap2, np.float32); leaf[:len(p)] = p
+    lv = [leaf.astype(np.float64)]
+    for k in range(1, G + 1):
+        bits = top_bits if k == G else 4
+        c = lv[-1].reshape(-1, 1 << bits)
+        c = np.concatenate([c, np.zeros((c.shape[0], 16 - c.shape[1]))], 1)
+        s1 = c[:, 0::2] + c[:, 1::2]; s2 = s1[:, 0::2] + s1[:, 1::2]; s3 = s2[:, 0::2] + s2[:, 1::2]
+        lv.append(s3[:, 0] + s3[:, 1])
+    return lv, G, top_bits
+
+
+def _r16_descend(lv, G, top_bits, u):
+    root = lv[G][0]
+    pos = root * u
+    node = 0
+    for k in range(G, 0, -1):
+        bits = top_bits if k == G else 4
+        c = np.zeros(16); c[:1 << bits] = lv[k - 1][node << bits:(node + 1) << bits]
+        s1 = c[0::2] + c[1::2]; s2 = s1[0::2] + s1[1::2]; s3 = s2[0::2] + s2[1::2]
+        ch = 0
+        for lvl_sums, width in ((s3, 8), (s2, 4), (s1, 2), (c, 1)):
+            base = ch // width          # index of the left child among this level's nodes
+            left, right = lvl_sums[base], lvl_sums[base + 1]
+            if not (pos < left or right == 0.0):
+                pos -= left
+                ch += width
+        node = (node << bits) | (ch & ((1 << bits) - 1))
+    return node
+
+
+@pytest.mark.parametrize("n", [2, 3, 13, 16, 100, 1000, 4096, 5000, 70000])
+def test_sparse_radix16_tree_equals_binary_sumtree(n):
+    from oracle import oracle as O
+    rng = np.random.default_rng(n)
+    p = ((np.abs(rng.standard_normal(n)).clip(max=1) + 1e-7) ** 0.6).astype(np.float32)
+    levels = max(1, (n - 1).bit_length())
+    lv, G, top_bits = _r16_model(p, levels)
+    t = O.SumTreeOracle(1 << levels); t.build(p)
+    assert lv[G][0] == t.total                                  # same fp64 root
+    for k in range(1, G):                                       # every stored level == the binary tree's level
+        d = levels - 4 * k
+        np.testing.assert_array_equal(lv[k], t.sum[1 << d:2 << d])
+    u = rng.random(300)
+    u[:3] = [0.0, 0.5, 1.0 - 2.0 ** -53]
+    want, _ = t.sample(u)
+    got = np.array([_r16_descend(lv, G, top_bits, x) for x in u])
+    np.testing.assert_array_equal(got, want)
