@@ -75,6 +75,9 @@ def parse():
                          "(PyTorch's default, which the reference runs, is fp32 matmul; the headline keeps fp32)")
     ap.add_argument("--log2n-build", type=int, default=23, help="also time the bulk tree build at this log2 N (0: skip)")
     ap.add_argument("--e2e-steps", type=int, default=200, help="steps per end-to-end segment (3 segments, median reported)")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling aid: only the device-resident loop (no per-kernel timing, e2e or CPU baseline); "
+                         "the line it prints is NOT a bench result")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=48)
     return ap.parse_args()
@@ -568,6 +571,11 @@ def main():
     value = B * world * args.steps / (ms / 1e3)
     scal = out["scalars"].tolist()
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "not_a_bench_result": True, "ms_per_step": ms / args.steps,
+                              "gpu_launches_per_step": per_step_launches}), flush=True)
+        return
     # ---- dominant hand-written kernels, each timed alone with CUDA events (graph of `reps`
     #      launches on distinct index sets -> no Python launch overhead, no L2 reuse of the rows) ----
     reps = 20
@@ -762,14 +770,15 @@ def main():
     # current learner step computes; every step still moves its own 29 MB H2D inside the timed region.
     # Every step's scalars (loss, mean target, mean weight) are read back to pinned host memory on a
     # D2H stream and consumed by the host one step later, so the host never idles the GPU.
-    learner.memory.begin_ingest(hs, hns, ha, hr, hd)
+    learner.memory.ingest(hs, hns, ha, hr, hd, hp)
 
     def e2e_step(i=[0]):
         k = i[0] & 1
         if i[0] > 0:   # the previous step's 12-byte read must leave `scalars` before the graph rewrites it
             torch.cuda.current_stream(dev).wait_event(d2h_done[k ^ 1])
-        learner.memory.commit_ingest(hp)                            # copy done -> priorities -> sampleable
-        learner.memory.begin_ingest(hs, hns, ha, hr, hd)            # H2D of the next 512 transitions (async)
+        # ONE C call: the batch copied during the previous step becomes sampleable, the slots of the next 512
+        # transitions are retired and their H2D copy starts on the library's copy stream (async)
+        learner.memory.ingest(hs, hns, ha, hr, hd, hp)
         o = learner.fused_step(use_graph=use_graph)
         step_done.record(torch.cuda.current_stream(dev))
         if i[0] > 0:                                                # consume the PREVIOUS step's result
@@ -816,9 +825,9 @@ def main():
            "segment_values": [B * world * k2 / (m / 1e3) for m, _ in segs],
            "h2d_GBs": h2d * k2 / (ms2 / 1e3) / 1e9, "host_ms_per_step": host_ms / k2, "ms_per_step": ms2 / k2,
            "host_thread_bound_to_gpu_numa_node": bool(bound),
-           "what": "Replay.commit_ingest + begin_ingest (512 new transitions from pinned host, H2D on the ingest "
-                   "stream overlapping the step) + Learner.fused_step() + per-step D2H of the step's scalars to pinned "
-                   "host memory (consumed by the host one step later); median of 3 segments"}
+           "what": "Replay.ingest (b2rl_replay_ingest_pipelined: 512 new transitions from pinned host, H2D on the library's "
+                   "copy stream overlapping the step, published by the next call) + Learner.fused_step() + per-step D2H "
+                   "of the step's scalars to pinned host memory (consumed by the host one step later); median of 3 segments"}
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------
     cpu = None

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b2rl_replay_reserve": (C.c_int, [c_vp, c_i64, C.POINTER(c_i64), c_vp]),
     "b2rl_replay_copy_payload": (C.c_int, [c_vp, C.POINTER(c_vp), c_i64, c_i64, c_vp]),
     "b2rl_replay_commit": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "b2rl_replay_ingest_pipelined": (C.c_int, [c_vp, C.POINTER(c_vp), c_vp, c_i64, c_vp]),
     "b2rl_replay_evict": (C.c_int, [c_vp, c_i64, c_vp]),
     "b2rl_replay_fill_hash": (C.c_int, [c_vp, c_i64, c_u32, c_vp]),
     "b2rl_tree_build": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),

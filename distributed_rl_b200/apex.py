@@ -197,6 +197,14 @@ class Replay(threading.Thread):
         """Ask the ingest thread to leave its loop (the reference's daemon thread can only die with the process)."""
         self._stop_evt.set()
 
+    def ingest(self, s, ns, a, r, d, p) -> None:
+        """Steady-state ingest, one call per learner iteration (b2rl_replay_ingest_pipelined): the batch handed
+        over by the previous call becomes sampleable, this one's host->device copy starts on the library's copy
+        stream and overlaps the learner step that follows.  All arguments pinned host (or device) tensors."""
+        with self._lock:
+            self.store.ingest_pipelined([s, ns, a, r, d], p)
+        self.total_frame += int(p.numel())
+
     def run(self):
         """Poll the actors' Redis list like APE_X/ReplayMemory.py:118-161: drain `experience`, push, honour the
         learner's eviction request (`lock`, :151-160).  Minibatches are assembled on demand by sample()."""

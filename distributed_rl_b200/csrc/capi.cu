@@ -35,6 +35,10 @@ static void free_all(b2rl_replay* h) {
   if (h->rng_dev) cudaFree(h->rng_dev);
   if (h->n_valid_dev) cudaFree(h->n_valid_dev);
   if (h->build_ticket) cudaFree(h->build_ticket);
+  if (h->pipe_prios) cudaFree(h->pipe_prios);
+  if (h->ev_reserved) cudaEventDestroy(h->ev_reserved);
+  if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+  if (h->ingest_stream) cudaStreamDestroy(h->ingest_stream);
 }
 
 extern "C" int b2rl_replay_create(const b2rl_replay_desc* d, b2rl_replay** out) {

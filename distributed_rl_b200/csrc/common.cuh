@@ -139,4 +139,10 @@ struct b2rl_replay {
   int64_t size = 0;       // valid slots
   int64_t head = 0;       // next slot to write
   int64_t reserved = 0;   // slots zeroed by b2rl_replay_reserve and not yet committed
+  // b2rl_replay_ingest_pipelined: library-owned copy stream + events, device staging of the pending priorities
+  cudaStream_t ingest_stream = nullptr;
+  cudaEvent_t ev_reserved = nullptr, ev_copied = nullptr;
+  float* pipe_prios = nullptr;
+  int64_t pipe_cap = 0;   // floats allocated at pipe_prios
+  int64_t pipe_n = 0;     // records of the batch whose copy is in flight (0: none)
 };

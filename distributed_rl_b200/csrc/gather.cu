@@ -471,6 +471,73 @@ extern "C" int b2rl_replay_commit(b2rl_replay* h, const float* prios, int64_t n,
   return B2RL_OK;
 }
 
+// One call per learner iteration for a steady ingest: publish the batch whose host->device copy was started by
+// the PREVIOUS call (the learner stream waits for that copy's event, then writes its priorities: the records
+// become sampleable), then retire the slots of the NEXT batch and start its copy on the library's own copy
+// stream — which therefore overlaps whatever the caller enqueues on `stream` next (the learner step).
+// The priorities travel with the payload and wait in device memory, so no host buffer has to outlive its copy
+// beyond the next call.  fields_src == NULL flushes: publishes the pending batch and starts nothing.
+extern "C" int b2rl_replay_ingest_pipelined(b2rl_replay* h, const void* const* fields_src, const float* prios_src,
+                                            int64_t n, void* stream) {
+  B2RL_REQUIRE(h != nullptr, "null handle");
+  B2RL_REQUIRE(fields_src == nullptr || (n >= 1 && n <= h->capacity && prios_src != nullptr), "bad batch");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->ingest_stream == nullptr) {
+    B2RL_CUDA(cudaStreamCreateWithFlags(&h->ingest_stream, cudaStreamNonBlocking));
+    B2RL_CUDA(cudaEventCreateWithFlags(&h->ev_reserved, cudaEventDisableTiming));
+    B2RL_CUDA(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+  }
+  if (h->pipe_n > 0) {                      // 1. publish the batch in flight
+    B2RL_REQUIRE(h->reserved == h->pipe_n, "pipelined ingest mixed with reserve/commit");
+    B2RL_CUDA(cudaStreamWaitEvent(st, h->ev_copied, 0));
+    const int64_t m = h->pipe_n;
+    h->size = (h->size + m > h->capacity) ? h->capacity : h->size + m;
+    int rc = b2rl_tree_update_impl(h, nullptr, h->head, h->pipe_prios, 0.0f, m, st, true);
+    if (rc != B2RL_OK) return rc;
+    h->head = (h->head + m) % h->capacity;
+    h->reserved = 0;
+    h->pipe_n = 0;
+    // the copy stream must not overwrite pipe_prios before this update has read it
+    B2RL_CUDA(cudaEventRecord(h->ev_reserved, st));
+    B2RL_CUDA(cudaStreamWaitEvent(h->ingest_stream, h->ev_reserved, 0));
+  }
+  if (fields_src == nullptr) return B2RL_OK;
+  B2RL_REQUIRE(h->reserved == 0, "a reservation is already pending (call b2rl_replay_commit first)");
+  if (h->pipe_cap < n) {                    // (re)grow the priority staging; rare, synchronous
+    B2RL_CUDA(cudaStreamSynchronize(h->ingest_stream));
+    B2RL_CUDA(cudaStreamSynchronize(st));
+    if (h->pipe_prios) cudaFree(h->pipe_prios);
+    h->pipe_prios = nullptr;
+    B2RL_CUDA(cudaMalloc((void**)&h->pipe_prios, sizeof(float) * (size_t)n));
+    h->pipe_cap = n;
+  }
+  // 2. retire the slots about to be overwritten (they can no longer be sampled)
+  const int64_t overwritten = h->size + n - h->capacity;
+  if (overwritten > 0) h->size -= overwritten;
+  int rc = b2rl_tree_update_impl(h, nullptr, h->head, nullptr, 0.0f, n, st, overwritten > 0);
+  if (rc != B2RL_OK) return rc;
+  h->reserved = n;
+  h->pipe_n = n;
+  // 3. payload + priorities on the copy stream, behind the retirement
+  B2RL_CUDA(cudaEventRecord(h->ev_reserved, st));
+  B2RL_CUDA(cudaStreamWaitEvent(h->ingest_stream, h->ev_reserved, 0));
+  const int64_t start = h->head;
+  const int64_t first = (start + n <= h->capacity) ? n : (h->capacity - start);
+  for (int f = 0; f < h->n_fields; ++f) {
+    const uint8_t* src = (const uint8_t*)fields_src[f];
+    if (src == nullptr) continue;
+    const int64_t rb = h->field_bytes[f];
+    B2RL_CUDA(cudaMemcpyAsync(h->field[f] + start * rb, src, (size_t)(first * rb), cudaMemcpyDefault, h->ingest_stream));
+    if (first < n)
+      B2RL_CUDA(cudaMemcpyAsync(h->field[f], src + first * rb, (size_t)((n - first) * rb), cudaMemcpyDefault,
+                                h->ingest_stream));
+  }
+  B2RL_CUDA(cudaMemcpyAsync(h->pipe_prios, prios_src, (size_t)n * sizeof(float), cudaMemcpyDefault, h->ingest_stream));
+  B2RL_CUDA(cudaEventRecord(h->ev_copied, h->ingest_stream));
+  return B2RL_OK;
+}
+
 extern "C" int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream) {
   B2RL_REQUIRE(h != nullptr, "null handle");
   B2RL_REQUIRE(delta >= 0 && delta <= h->size, "delta out of range (0..size)");

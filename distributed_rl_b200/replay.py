@@ -214,6 +214,30 @@ class DeviceReplay:
         self._inflight = keep + [pr]
         self._pending = None
 
+    def ingest_pipelined(self, fields: Sequence | None, priorities=None) -> None:
+        """One C call per iteration (b2rl_replay_ingest_pipelined): publish the batch copied during the previous
+        step, retire the next batch's slots, start its host->device copy on the library's copy stream.
+        `fields`: pinned host (or device) tensors in field order, `priorities`: fp32[n]; fields None = flush."""
+        if fields is None:
+            check(self.lib.b2rl_replay_ingest_pipelined(self._h, None, None, 0, self._st()))
+            self._pipe_keep = None
+            return
+        key = tuple(t.data_ptr() for t in fields) + (priorities.data_ptr(),)
+        cache = getattr(self, "_pipe_cache", None)
+        if cache is None or cache[0] != key:          # pointer array built once per set of staging buffers
+            ptrs = (C.c_void_p * _lib.MAX_FIELDS)()
+            n = None
+            for i, (f, t) in enumerate(zip(self.fields, fields)):
+                assert t.dtype == f.dtype and t.is_contiguous()
+                n = t.shape[0] if n is None else n
+                assert t.numel() * t.element_size() == n * f.nbytes, f"bad shape for {f.name}"
+                ptrs[i] = t.data_ptr()
+            assert priorities.dtype == torch.float32 and priorities.numel() == n and priorities.is_contiguous()
+            cache = self._pipe_cache = (key, ptrs, int(n))
+        _, ptrs, n = cache
+        check(self.lib.b2rl_replay_ingest_pipelined(self._h, ptrs, priorities.data_ptr(), n, self._st()))
+        self._pipe_keep = (fields, priorities)        # host buffers stay alive until the next call
+
     def evict(self, delta: int) -> None:
         check(self.lib.b2rl_replay_evict(self._h, int(delta), self._st()))
 

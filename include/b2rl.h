@@ -91,6 +91,18 @@ int b2rl_replay_copy_payload(b2rl_replay* h, const void* const* fields_src, int6
                              void* stream);
 int b2rl_replay_commit(b2rl_replay* h, const float* prios, int64_t n, void* stream);
 
+/* The steady-state form of the ingest loop of Replay.run (APE_X/ReplayMemory.py:128-139: drain -> PER.push) as ONE
+ * call per learner iteration: (1) the batch whose host->device copy the previous call started is published —
+ * `stream` waits for that copy, then its priorities are written (PER.push's priority append, baseline/PER.py:69-75);
+ * (2) the ring slots of the next batch are retired (priority 0: unsampleable while they are overwritten) and its
+ * payload + priorities are copied on a library-owned copy stream, overlapping whatever is enqueued on `stream`
+ * next.  Host buffers (pinned) must stay valid and unmodified until their copy has executed (the call is
+ * asynchronous: synchronize `stream` after the NEXT call, or keep enough staging sets).  fields_src == NULL:
+ * publish only (flush).
+ * Do not interleave with b2rl_replay_reserve / b2rl_replay_commit. */
+int b2rl_replay_ingest_pipelined(b2rl_replay* h, const void* const* fields_src, const float* prios_src, int64_t n,
+                                 void* stream);
+
 /* PER.remove_to_fit (baseline/PER.py:118-127): drop the `delta` oldest
  * records (priority := 0 so they can never be sampled; size -= delta). */
 int b2rl_replay_evict(b2rl_replay* h, int64_t delta, void* stream);

@@ -184,6 +184,48 @@ def test_pipelined_ingest_matches_ring_model(R):
     rep.close()
 
 
+def test_single_call_pipelined_ingest_matches_ring_model(R):
+    """b2rl_replay_ingest_pipelined: call k publishes batch k-1 and starts the copy of batch k; the ring, the
+    priorities and the payload equal PER.push applied one call later; slots in flight are never sampled."""
+    cap, n = 512, 96
+    rng = np.random.default_rng(18)
+    fields = (R.Field("x", torch.uint8, (64,)), R.Field("a", torch.int32, ()))
+    rep = R.DeviceReplay(cap, fields=fields)
+    model = O.RingModel(cap)
+    store = np.zeros((cap, 64), np.uint8)
+    bufs = [(torch.empty(n, 64, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(),
+             torch.empty(n, dtype=torch.float32).pin_memory()) for _ in range(2)]
+    pending = None
+    for step in range(11):     # wraps the ring twice
+        x, a, p = bufs[step & 1]
+        x.copy_(torch.from_numpy(rng.integers(0, 256, size=(n, 64), dtype=np.uint8)))
+        a.copy_(torch.from_numpy(rng.integers(0, 6, size=n).astype(np.int32)))
+        p.copy_(torch.from_numpy(_rand_prios(rng, n)))
+        rep.ingest_pipelined([x, a], p)
+        if pending is not None:                 # the previous batch is published by this call
+            slots_prev, x_prev, p_prev = pending
+            model.push(p_prev); store[slots_prev] = x_prev
+        slots = (model.head + np.arange(n)) % cap
+        pr = rep.priorities().cpu().numpy()
+        assert (pr[slots] == 0).all()                                  # retired before the copy may land
+        keep = np.setdiff1d(np.arange(cap), slots)
+        np.testing.assert_array_equal(pr[keep], model.prios[keep])
+        assert len(rep) == min(model.size, cap - n) and rep.head == model.head
+        if model.size:
+            idx, _, _ = rep.sample(256)
+            assert not np.isin(idx.cpu().numpy(), slots).any()         # never sampled while being overwritten
+            np.testing.assert_array_equal(rep.gather(idx)["x"].cpu().numpy(), store[idx.cpu().numpy()])
+        pending = (slots, x.numpy().copy(), p.numpy().copy())
+    rep.ingest_pipelined(None)                  # flush: publish the last batch
+    slots_prev, x_prev, p_prev = pending
+    model.push(p_prev); store[slots_prev] = x_prev
+    assert len(rep) == model.size and rep.head == model.head
+    np.testing.assert_array_equal(rep.priorities().cpu().numpy(), model.prios)
+    idx, _, _ = rep.sample(512)
+    np.testing.assert_array_equal(rep.gather(idx)["x"].cpu().numpy(), store[idx.cpu().numpy()])
+    rep.close()
+
+
 def test_empty_replay_sampling_is_an_error(R):
     from distributed_rl_b200._lib import B2RLError
     rep = R.DeviceReplay(16, fields=())
