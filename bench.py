@@ -838,6 +838,10 @@ def main():
                "sample": f"{r['cycles']} cycle(s) x {r['m']} train steps x batch {B} at N=2^{args.log2n} priorities "
                          f"(pool of 2048 pickled records), {r['seconds']:.1f} s of CPU work",
                "parts_s_per_cycle": r["parts"]}
+        try:        # the reference's own CPU-runnable case, flat PER store and SumTree store
+            cpu["c1_reference_case"] = cpu_c1_legs(r["cores"])
+        except Exception as e:  # noqa: BLE001 — a baseline leg must never take the bench line down
+            cpu["c1_reference_case"] = {"error": repr(e)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

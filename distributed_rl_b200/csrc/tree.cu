@@ -390,19 +390,26 @@ __device__ __forceinline__ int64_t node_of(const TreeView& t, int k, int64_t lea
 }
 
 // Small batch (n <= 512 per launch): ONE CTA.
-//   0. slot ids -> shared memory; the last occurrence of a slot in the batch is its winner
-//      (baseline/PER.py:42); winners write their leaves
-//   1. stored levels 1..ks (the levels with more than US_SMEM_NODES nodes, plus the first one that fits):
-//      one global round trip each — the node is recomputed from its 16 children by the first of the
-//      neighbouring entries that share it
-//   2. level ks was preloaded into shared memory at kernel start and is patched with the new values;
-//      every level above it is recomputed for ALL of its (<= 256) nodes from shared memory — no further
-//      global round trips, no contention on the few top nodes
+//   0. slot ids -> shared memory, chained into a 1024-bucket hash table (atomicExch on the bucket head): the
+//      last occurrence of a slot in the batch is its winner (baseline/PER.py:42) and is found by walking one
+//      short chain (a linear scan of the batch cost 5.5 k cycles, this 0.9 k); winners write their leaves
+//   1. stored levels 1..ks (the levels with more than US_SMEM_NODES nodes, plus the first one that fits): one
+//      global round trip each — the node is recomputed from its 16 children by the first of the neighbouring
+//      entries that share it (L1-cached loads: the CTA is the only writer, __syncthreads orders them)
+//   2. level ks was preloaded into shared memory at kernel start and is patched with the new values; every
+//      level above it is recomputed for ALL of its (<= 256) nodes from shared memory (rows padded to 17
+//      entries: conflict-free) — no further global round trips, no contention on the few top nodes
 // 2^20 leaves: 2 global round trips (65536- and 4096-node levels) + 3 shared-memory levels.
+// (A variant with 16 lanes per node and shuffle butterflies was measured slower: 16 passes of shuffles cost
+//  more issue slots than the 16-byte loads they saved.)
 constexpr int US_THREADS = 512;
-constexpr int US_SMEM_NODES = 4096;                 // 32 KB sums + 16 KB mins
-constexpr int US_TOP_NODES = US_SMEM_NODES / 16 + 32;   // all nodes of the levels above ks (256 + 16 + 1 ...)
-constexpr size_t US_SMEM_BYTES = US_SMEM_NODES * 12 + US_TOP_NODES * 12 + US_THREADS * 4;
+constexpr int US_SMEM_NODES = 4096;                         // level ks: up to 4096 nodes
+constexpr int US_PAD_NODES = US_SMEM_NODES + US_SMEM_NODES / 16;   // rows of 16 children padded to 17
+constexpr int US_TOP_NODES = 256 + 16 + 16 + 16 + 16;       // all nodes of the levels above ks, each level padded
+constexpr int US_BUCKETS = 1024;
+constexpr size_t US_SMEM_BYTES = (size_t)(US_PAD_NODES + US_TOP_NODES) * 12 + US_THREADS * 4 + US_BUCKETS * 4 + US_THREADS * 4;
+
+__device__ __forceinline__ int us_pad(int i) { return i + (i >> 4); }
 
 __global__ void __launch_bounds__(US_THREADS, 1)
 k_update_small(const __grid_constant__ TreeView t, const int64_t* __restrict__ idx, int64_t ring_start,
@@ -411,11 +418,13 @@ k_update_small(const __grid_constant__ TreeView t, const int64_t* __restrict__ i
 #define US_PROBE(i) do { if (probe != nullptr && threadIdx.x == 0) probe[i] = clock64(); } while (0)
   extern __shared__ __align__(16) unsigned char us_smem[];
   US_PROBE(0);
-  double* s_sum = reinterpret_cast<double*>(us_smem);                     // level ks
-  double* s_top = s_sum + US_SMEM_NODES;                                  // levels > ks, packed
-  float* s_min = reinterpret_cast<float*>(s_top + US_TOP_NODES);          // level ks
-  float* s_topm = s_min + US_SMEM_NODES;
+  double* s_sum = reinterpret_cast<double*>(us_smem);                     // level ks (padded rows)
+  double* s_top = s_sum + US_PAD_NODES;                                   // levels > ks, packed (padded rows)
+  float* s_min = reinterpret_cast<float*>(s_top + US_TOP_NODES);
+  float* s_topm = s_min + US_PAD_NODES;
   int32_t* s_j = reinterpret_cast<int32_t*>(s_topm + US_TOP_NODES);
+  int32_t* s_head = s_j + US_THREADS;
+  int32_t* s_next = s_head + US_BUCKETS;
   const int tid = threadIdx.x;
   if (n_valid_dev != nullptr && tid == 0) *n_valid_dev = n_valid_new;   // ring size after this ingest step
   int32_t j = -1;
@@ -424,25 +433,25 @@ k_update_small(const __grid_constant__ TreeView t, const int64_t* __restrict__ i
     if (jj >= 0 && jj < capacity) j = (int32_t)jj;    // out-of-range indices are ignored
   }
   s_j[tid] = j;
+  s_head[tid] = -1; s_head[tid + US_THREADS] = -1;
   // preload stored level ks (old values; the touched entries are patched below)
-  const int64_t nks = (ks == t.G) ? 1 : (t.cap2 >> (4 * ks));
-  for (int64_t i = tid; i < nks; i += US_THREADS) {
-    s_sum[i] = __ldcg(t.sum + t.off[ks] + i);
-    s_min[i] = __ldcg(t.minv + t.off[ks] + i);
+  const int nks = (ks == t.G) ? 1 : (int)(t.cap2 >> (4 * ks));
+  for (int i = tid; i < nks; i += US_THREADS) {
+    s_sum[us_pad(i)] = t.sum[t.off[ks] + i];
+    s_min[us_pad(i)] = t.minv[t.off[ks] + i];
   }
   const float myval = (j >= 0 && vals != nullptr) ? vals[tid] : const_val;
   __syncthreads();
   US_PROBE(1);
+  const unsigned bucket = (unsigned)(lowbias32((uint32_t)j) & (US_BUCKETS - 1));
+  if (idx != nullptr) {      // ring ranges have no duplicates
+    if (j >= 0) s_next[tid] = atomicExch(s_head + bucket, tid);
+    __syncthreads();
+  }
   if (j >= 0) {
-    int dup = 0;                                            // does a LATER entry name the same slot?
-    if (idx != nullptr) {
-      for (int q = tid + 1; q < n && (q & 3); ++q) dup |= (s_j[q] == j);
-#pragma unroll 4
-      for (int q = (tid + 4) & ~3; q < n; q += 4) {         // s_j[n..] = -1 never matches
-        const int4 v = *reinterpret_cast<const int4*>(s_j + q);
-        dup |= (v.x == j) | (v.y == j) | (v.z == j) | (v.w == j);
-      }
-    }
+    bool dup = false;                                       // does a LATER entry name the same slot?
+    if (idx != nullptr)
+      for (int q = s_head[bucket]; q >= 0; q = s_next[q]) dup = dup || (q > tid && s_j[q] == j);
     if (!dup) t.leaf[j] = myval;
   }
   US_PROBE(2);
@@ -458,12 +467,12 @@ k_update_small(const __grid_constant__ TreeView t, const int64_t* __restrict__ i
       }
       if (mine) {
         double c[16];
-        load_child_sums<true>(t, k, node, c);
-        const float m = load_child_min<true>(t, k, node);
+        load_child_sums<false>(t, k, node, c);
+        const float m = load_child_min<false>(t, k, node);
         const double v = pairwise16(c);
         t.sum[t.off[k] + node] = v;
         t.minv[t.off[k] + node] = m;
-        if (k == ks) { s_sum[node] = v; s_min[node] = m; }
+        if (k == ks) { s_sum[us_pad((int)node)] = v; s_min[us_pad((int)node)] = m; }
       }
     }
     __syncthreads();
@@ -475,26 +484,27 @@ k_update_small(const __grid_constant__ TreeView t, const int64_t* __restrict__ i
   int top_off = 0;
   for (int k = ks + 1; k <= t.G; ++k) {
     const int bits = (k == t.G) ? t.top_bits : 4;
-    const int64_t nk = (k == t.G) ? 1 : (t.cap2 >> (4 * k));
+    const int nk = (k == t.G) ? 1 : (int)(t.cap2 >> (4 * k));
     if (tid < nk) {
       double c[16];
       float m = INFINITY;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const bool in = i < (1 << bits);
-        c[i] = in ? c_sum[((int64_t)tid << bits) + i] : 0.0;
-        m = fminf(m, in ? c_min[((int64_t)tid << bits) + i] : INFINITY);
+        const int ci = us_pad((tid << bits) + i);           // children rows are padded: (tid*16+i) + tid
+        c[i] = in ? c_sum[ci] : 0.0;
+        m = fminf(m, in ? c_min[ci] : INFINITY);
       }
       const double v = pairwise16(c);
-      s_top[top_off + tid] = v;
-      s_topm[top_off + tid] = m;
+      s_top[top_off + us_pad(tid)] = v;
+      s_topm[top_off + us_pad(tid)] = m;
       t.sum[t.off[k] + tid] = v;
       t.minv[t.off[k] + tid] = m;
     }
     __syncthreads();
     c_sum = s_top + top_off;
     c_min = s_topm + top_off;
-    top_off += (int)nk;
+    top_off += us_pad(nk) + 1;
   }
   US_PROBE(12);
 #undef US_PROBE

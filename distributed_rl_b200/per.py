@@ -79,9 +79,11 @@ class PER:
         return self.store.gather(idx), prob, idx, w
 
     def remove_to_fit(self):
-        """FIFO drop (:118-127).  The ring already overwrites the oldest slot on push, so there is
-        never more than `maxlen` to drop; kept for API compatibility."""
-        return None
+        """FIFO drop of everything beyond `maxlen` (:118-127) = b2rl_replay_evict of the oldest records.  The
+        ring overwrites its oldest slot on push, so with capacity == maxlen there is normally nothing to drop."""
+        over = len(self.store) - self.maxlen
+        if over > 0:
+            self.store.evict(over)
 
     @property
     def max_weight(self) -> float:
@@ -119,7 +121,10 @@ class PrioritizedMemory:
                           torch.as_tensor(np.asarray(priorities, np.float32)))
 
     def remove_to_fit(self):
-        return None      # ring: never over capacity
+        """popleft() until len <= capacity (baseline/utils.py:352-357) = evict the oldest records."""
+        over = len(self.store) - self.capacity
+        if over > 0:
+            self.store.evict(over)
 
     def __len__(self):
         return len(self.store)
