@@ -59,30 +59,41 @@ class FlatGradBucket:
             off += p.numel()
         n_early = sum(p.numel() for p in early)
         self._early, self._late = self.flat[:n_early], self.flat[n_early:]
-        self._pending, self._seen, self._work = len(early), 0, None
+        self._pending, self._work = len(early), None
+        self._ready = set()                 # ids of the early params whose gradient is complete this step
+        self._sink_attached = False
         gloo = dist.is_initialized() and dist.get_backend() != "nccl"
 
-        def hook(_p):
-            self._seen += 1
-            if self._seen == self._pending and world() > 1:
+        def mark(p):
+            self._ready.add(id(p))          # a set: a parameter reported twice still counts once
+            if len(self._ready) == self._pending and self._work is None and world() > 1:
                 self._work = self._reduce(self._early, async_op=True)
                 self._early_needs_div = gloo
 
-        self._early_hook, self._early_params = hook, early
+        def autograd_hook(p):
+            # torch >= 2.x runs post-accumulate-grad hooks even when a custom Function returned None for the
+            # parameter (nothing was accumulated).  With a WeightGradSink attached the early gradients never come
+            # through autograd — the sink reports them AFTER its own accumulation — so this path must stay silent,
+            # or the all-reduce would start before the late-arriving gradients exist.
+            if not self._sink_attached:
+                mark(p)
+
+        self._early_hook, self._early_params = mark, early
         for p in early:
-            p.register_post_accumulate_grad_hook(hook)
+            p.register_post_accumulate_grad_hook(autograd_hook)
 
     def attach_sink(self, sink) -> None:
         """Weight gradients that bypass autograd's AccumulateGrad (linear.WeightGradSink) report here instead:
         the early all-reduce is then launched from the sink's side stream as soon as the last early gradient
         has been accumulated there."""
+        self._sink_attached = True
         for p in getattr(self, "_early_params", []):
             sink.on_ready[id(p)] = self._early_hook
 
     def finish(self) -> None:
         """After backward: reduce the late (small) part, then wait for the early part."""
         if world() == 1:
-            self._seen = 0
+            self._ready.clear() if hasattr(self, "_ready") else None
             return
         if self._late.numel():
             self._reduce(self._late)
@@ -92,7 +103,8 @@ class FlatGradBucket:
                 self._early.div_(world())
         else:                                       # hooks did not fire (no early grads): reduce now
             self._reduce(self._early)
-        self._work, self._seen = None, 0
+        self._work = None
+        self._ready.clear()
 
 
 def all_reduce_max_(x: torch.Tensor, async_op: bool = False):

@@ -80,20 +80,23 @@ def main():
     idx_dp, w_dp, g_dp = one_step_grads(L, glob)
 
     # ---- single-process reference: every shard on THIS GPU, no collective ---------------------------
-    g_sum = None
+    g_sum, g_own = None, None
     for shard in range(world):
         Lr = make_learner(); fill(Lr, shard)
         idx_r, w_r, g_r = one_step_grads(Lr, glob)
         if shard == rank:
             assert torch.equal(idx_r, idx_dp) and torch.equal(w_r, w_dp)     # local sampling is shard-local
+            g_own = g_r
         g_sum = g_r if g_sum is None else [a + b for a, b in zip(g_sum, g_r)]
         del Lr
     names = [n for n, _ in L.model.named_parameters()]
-    worst = 0.0
-    for n, a, b in zip(names, g_dp, g_sum):
+    worst, bad = 0.0, []
+    for n, a, b, own in zip(names, g_dp, g_sum, g_own):
         r = rel(a, b / world)
         worst = max(worst, r)
-        assert r <= 1e-5, (n, r)
+        if r > 1e-5:
+            bad.append(f"{n}: vs mean {r:.3e}, vs own shard {rel(a, own):.3e}, vs sum {rel(a, b):.3e}")
+    assert not bad, "rank %d: %s" % (rank, "; ".join(bad))
 
     # ---- step loop: the IS-weight normaliser is the MAX reduced during the previous step ------------------
     st = L.memory.store

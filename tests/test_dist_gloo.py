@@ -74,6 +74,39 @@ def _worker(rank, world, port, q):
         dist.all_gather(g, r.grad)
         ok3 = ok3 and bool(torch.allclose(p.grad, sum(g) / world, atol=1e-6))
     out["sink_ok"] = ok3
+    # 1d. regression (round 1, found by tests/test_gpu_20_multigpu.py): torch runs post-accumulate-grad hooks even
+    #     when a custom Function returns None for a parameter.  With a sink attached those calls must not count:
+    #     the early all-reduce may only start after the sink has reported EVERY early gradient.
+    class _NoWeightGrad(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.save_for_backward(x, w)
+            return x @ w.T
+
+        @staticmethod
+        def backward(ctx, gy):
+            x, w = ctx.saved_tensors
+            return gy @ w, None                         # dL/dW is produced "elsewhere" (the sink)
+
+    wa = torch.nn.Parameter(torch.randn(3, 4)); wb = torch.nn.Parameter(torch.randn(2, 3))
+    b4 = D.FlatGradBucket([wa, wb])
+    b4.enable_overlap([wa, wb])
+
+    class _Sink4:
+        on_ready = {}
+    b4.attach_sink(_Sink4)
+    x4 = torch.randn(5, 4, requires_grad=True)
+    _NoWeightGrad.apply(_NoWeightGrad.apply(x4, wa), wb).sum().backward()    # fires both autograd hooks, no grads
+    started_early = b4._work is not None
+    ga, gb = torch.full_like(wa, float(rank + 1)), torch.full_like(wb, float(2 * rank + 1))
+    wb.grad.add_(gb); _Sink4.on_ready[id(wb)](wb)
+    after_one = b4._work is not None
+    wa.grad.add_(ga); _Sink4.on_ready[id(wa)](wa)
+    b4.finish()
+    mean_a = sum(float(r + 1) for r in range(world)) / world
+    mean_b = sum(float(2 * r + 1) for r in range(world)) / world
+    out["none_grad_hooks_ok"] = (not started_early) and (not after_one) and \
+        bool(torch.allclose(wa.grad, torch.full_like(wa, mean_a))) and bool(torch.allclose(wb.grad, torch.full_like(wb, mean_b)))
     # 2. priority-max reduction: shard-local IS weights / global max == single-replay formula
     n, beta = 1024, 0.4
     rng = np.random.default_rng(100 + rank)
@@ -118,6 +151,7 @@ def test_world2_gloo_data_parallel_logic():
         assert res[r]["bucket_ok"] and res[r]["views_ok"] and res[r]["isw_ok"] and res[r]["shard_ok"], res[r]
         assert res[r]["overlap_ok"], res[r]
         assert res[r]["sink_ok"], res[r]
+        assert res[r]["none_grad_hooks_ok"], res[r]
     assert res[0]["mw"] == res[1]["mw"]
 
 
