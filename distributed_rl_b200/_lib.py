@@ -55,6 +55,8 @@ SIGNATURES = {
     "b2rl_gemm_packed_floats": (c_i64, [c_i64, c_i64, c_i32]),
     "b2rl_gemm_split_pack": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "b2rl_gemm_split_pack_into": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),
+    "b2rl_gemm_pack_act_nhwc": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "b2rl_unflatten_relu_mask": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "b2rl_gemm_workspace_floats": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "b2rl_gemm_tf32x3": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "b2rl_dueling_forward": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),

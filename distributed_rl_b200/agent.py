@@ -106,12 +106,22 @@ class ConvStack(nn.Sequential):
         return (c.in_channels, c.kernel_size, c.stride, c.padding, c.bias) == (4, (8, 8), (4, 4), (0, 0), None) \
             and c.out_channels in (16, 32)
 
-    def forward_tail(self, y, relu_applied: bool):
-        """Continue after conv_1: `y` is conv_1's output (pre- or post-ReLU)."""
+    def forward_tail(self, y, relu_applied: bool, stop_before_head: bool = False):
+        """Continue after conv_1: `y` is conv_1's output (pre- or post-ReLU).  stop_before_head: return the LAST
+        conv's pre-ReLU output instead of running the closing ReLU + Flatten (ends_with_relu_flatten() must hold):
+        linear.relu_flat_linear3x folds those two into the heads' operand packing."""
+        layers = list(self.children())[2 if relu_applied else 1:]
+        if stop_before_head:
+            layers = layers[:-2]
         x = y
-        for layer in list(self.children())[2 if relu_applied else 1:]:
+        for layer in layers:
             x = self._run(layer, x)
         return x
+
+    def ends_with_relu_flatten(self) -> bool:
+        layers = list(self.children())
+        return (len(layers) >= 4 and isinstance(layers[-3], nn.Conv2d) and isinstance(layers[-2], nn.ReLU)
+                and isinstance(layers[-1], nn.Flatten))
 
 
 class DenseStack(nn.Sequential):
@@ -129,10 +139,19 @@ class DenseStack(nn.Sequential):
             if a is not None:
                 self.add_module(f"act_{i + 1}", a)
 
+    dense_3xtf32 = False      # bias-free wide layers through linear.linear3x (set by GraphAgent / the learner)
+
+    def _layer(self, layer, x):
+        if (self.dense_3xtf32 and isinstance(layer, nn.Linear) and layer.bias is None and x.is_cuda and x.dim() == 2
+                and x.dtype == torch.float32 and layer.out_features >= 64 and layer.in_features >= 64):
+            from .linear import linear3x          # fp32 SIMT sgemm -> 3xTF32 tcgen05 GEMM at fp32 accuracy
+            return linear3x(x, layer.weight)
+        return layer(x)
+
     def forward(self, xs):
         x = xs[0] if isinstance(xs, (tuple, list)) else xs
         for layer in self:
-            x = layer(x)
+            x = self._layer(layer, x)
         return x
 
     def forward_after_first(self, h):
@@ -186,6 +205,13 @@ class ViewAs(nn.Module):
         shape, x = xs[0], xs[1]
         dims = tuple(int(v) for v in (shape.tolist() if torch.is_tensor(shape) else shape))
         return x.view(dims)
+
+
+class _PreHead:
+    """Marker for a conv stack's output that has NOT been through its closing ReLU + Flatten yet."""
+
+    def __init__(self, y):
+        self.y = y
 
 
 class _Add(nn.Module):
@@ -244,6 +270,7 @@ class GraphAgent(nn.Module):
         # Dueling tail: two 2-layer heads (relu, linear) combined by Add / Mean / Substract nodes
         # (cfg/ape_x.json:52-88) -> one kernel after the shared first layer (csrc/dueling.cu).
         self.fused_dueling_tail = False
+        self.fused_relu_flatten = True      # act_3 + Flatten folded into the heads' operand packs (linear._ReluFlatLinear3x)
         self._dueling = {}
         for g in set(self._head_groups.values()):
             d = self._match_dueling(g)
@@ -294,6 +321,16 @@ class GraphAgent(nn.Module):
                     from .linear import dueling_tail, dueling_tail_supported, linear3x
                     x = vals[self._prev[name][0]]
                     adv, val = getattr(self, duel["adv"]), getattr(self, duel["val"])
+                    pre = x if isinstance(x, _PreHead) else None
+                    if pre is not None:
+                        from .linear import relu_flat_linear3x
+                        ws = [adv.MLP_1.weight, val.MLP_1.weight]
+                        cache = None if self._pack_cache is None else self._pack_cache.setdefault(group, {})
+                        h = relu_flat_linear3x(pre.y, ws, cache)
+                        vals[duel["out"]] = dueling_tail(h, adv.MLP_2.weight, val.MLP_2.weight)
+                        for n in duel["inner"]:
+                            vals[n] = None
+                        continue
                     if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32:
                         ws = [adv.MLP_1.weight, val.MLP_1.weight]
                         if self.dense_3xtf32:
@@ -322,7 +359,10 @@ class GraphAgent(nn.Module):
                 vals[name] = getattr(self, name).forward_after_first(first_out[name])
                 continue
             srcs = [inputs[i] for i in self._ext[name]] + [vals[p] for p in self._prev[name]]
-            vals[name] = getattr(self, name)(tuple(srcs))
+            node = getattr(self, name)
+            if isinstance(node, DenseStack):
+                node.dense_3xtf32 = self.dense_3xtf32
+            vals[name] = node(tuple(srcs))
         return tuple(vals[n] for n in self._outputs)
 
     @contextlib.contextmanager
@@ -350,6 +390,33 @@ class GraphAgent(nn.Module):
                 self._pack_cache.setdefault(group, {})["bwdT" if transposed else "fwd"] = \
                     _pack_pieces([w.detach() for w in ws], transposed, True)
 
+    def _prehead_group(self):
+        """(group, (C, HW)) if the first conv node ends with [Conv2d, ReLU, Flatten] and feeds ONLY one dueling head
+        group that runs on the 3xTF32 + fused-tail path — then ReLU + Flatten can be folded into the heads'
+        operand packs (linear.relu_flat_linear3x); else None.  (C, HW) is resolved lazily from the last conv.)"""
+        if not (self.fused_relu_flatten and self.dense_3xtf32 and self.fused_dueling_tail and self.fuse_sibling_heads):
+            return None
+        name = self.first_conv_node()
+        if name is None or not getattr(self, name).ends_with_relu_flatten() or name in self._outputs:
+            return None
+        users = [m for m in self._order if name in self._prev[m]]
+        groups = {self._head_groups.get(u) for u in users}
+        if len(groups) != 1 or None in groups:
+            return None
+        group = groups.pop()
+        if sorted(users) != sorted(group) or group not in self._dueling:
+            return None
+        conv = list(getattr(self, name).children())[-3]
+        adv, val = (getattr(self, self._dueling[group][r]) for r in ("adv", "val"))
+        wa, wv = adv.MLP_2.weight, val.MLP_2.weight
+        if wv.shape != (1, wa.shape[1]) or wa.shape[1] % 32 or wa.shape[1] > 1024 or wa.shape[0] > 32:
+            return None                                   # the fused dueling tail (csrc/dueling.cu) would not take it
+        k = adv.MLP_1.in_features
+        c = conv.out_channels
+        if k % c:
+            return None
+        return group, (c, k // c)
+
     def first_conv_node(self):
         """Name of the CNN2D node fed by external input 0, if it starts with the Atari conv_1."""
         for name in self._order:
@@ -361,7 +428,20 @@ class GraphAgent(nn.Module):
     def forward_from_conv1(self, y, relu_applied: bool, extra_inputs=()):
         """Forward pass given conv_1's output of the first CNN2D node (fused gather+conv1 kernel)."""
         name = self.first_conv_node()
-        feat = getattr(self, name).forward_tail(y, relu_applied)
+        stack = getattr(self, name)
+        if y.is_cuda and self._prehead_group() is not None:
+            from .linear import relu_flat_supported
+            y_last = stack.forward_tail(y, relu_applied, stop_before_head=True)
+            group = self._prehead_group()[0]
+            ws = [getattr(self, n).MLP_1.weight for n in (self._dueling[group]["adv"], self._dueling[group]["val"])]
+            if relu_flat_supported(y_last, ws):
+                return self.forward([None, *extra_inputs], preset={name: _PreHead(y_last)})
+            layers = list(stack.children())[-2:]                 # not channels_last after all: finish the stack
+            feat = y_last
+            for layer in layers:
+                feat = stack._run(layer, feat)
+            return self.forward([None, *extra_inputs], preset={name: feat})
+        feat = stack.forward_tail(y, relu_applied)
         return self.forward([None, *extra_inputs], preset={name: feat})
 
     # -- the surface the learners call --------------------------------------------

@@ -133,6 +133,114 @@ k_split_pack(const float* __restrict__ src, int src_rows, int src_cols, int64_t 
   *reinterpret_cast<float4*>(out + term_stride + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// ---- activation-side packs that fold act_3 (ReLU) + nn.Flatten into the heads' operand images ----------------
+// The conv stack's output is NHWC in memory: y[b][hw][c].  The reference flattens the logical NCHW tensor
+// (baseline/baseNetwork.py:204-209), so the heads' weights index features as f = c*HW + hw.  Instead of a ReLU
+// kernel plus a permuting copy per pass, these kernels read y coalesced, transpose through shared memory and write
+// the operand images in f order directly (the weights' packs stay as they are).
+//   k_pack_act_nhwc<false>: A-role image of x = relu(y) viewed [B][K = C*HW]          (forward)
+//   k_pack_act_nhwc<true> : B-role image of x^T [K rows][contraction B]               (weight gradient)
+//   k_unflatten_relu_mask : dL/dy[b][hw][c] = gx[b][c*HW + hw] * (y[b][hw][c] > 0)    (input gradient)
+constexpr int ACT_PAD = 1;      // shared-memory row padding: kills the bank conflicts of the transposed reads
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(256)
+k_pack_act_nhwc(const float* __restrict__ y, int B, int HW, int C, int relu, float* __restrict__ out,
+                int rows_pad, int k_chunks) {
+  extern __shared__ float s_act[];
+  const int K = C * HW;
+  if (!TRANSPOSE) {
+    // one CTA per image row b (rows >= B are zero padding): s[hw][c], row stride C + 1
+    const int b = blockIdx.x;
+    const int ld = C + ACT_PAD;
+    if (b < B) {
+      const float* src = y + (int64_t)b * K;
+      for (int i = threadIdx.x; i < K; i += 256) {
+        float v = src[i];
+        if (relu) v = fmaxf(v, 0.0f);
+        s_act[(i / C) * ld + (i % C)] = v;
+      }
+    }
+    __syncthreads();
+    const int rt = b / TM, rr = b - rt * TM, tiles = rows_pad / TM;
+    const int64_t term_stride = (int64_t)k_chunks * rows_pad * 32;
+    for (int w = threadIdx.x; w < k_chunks * 8; w += 256) {
+      const int kc = w >> 3, unit = w & 7;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int f = kc * KC + unit * 4 + e;
+        v[e] = (b < B && f < K) ? s_act[(f % HW) * ld + (f / HW)] : 0.0f;
+      }
+      float hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
+      const int64_t off = (((int64_t)kc * tiles + rt) * TM + rr) * 32 + ((unit ^ (rr & 7)) << 2);
+      *reinterpret_cast<float4*>(out + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(out + term_stride + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  } else {
+    // one CTA per (chunk of 32 b's, hw): s[b][c], row stride C + 1; image rows f = c*HW + hw, contraction = b
+    const int kc = blockIdx.x, hw = blockIdx.y;
+    const int ld = C + ACT_PAD;
+    for (int i = threadIdx.x; i < 32 * C; i += 256) {
+      const int bb = i / C, c = i - bb * C, b = kc * KC + bb;
+      float v = (b < B) ? y[((int64_t)b * HW + hw) * C + c] : 0.0f;
+      if (relu) v = fmaxf(v, 0.0f);
+      s_act[bb * ld + c] = v;
+    }
+    __syncthreads();
+    const int tiles = rows_pad / TN;
+    const int64_t term_stride = (int64_t)k_chunks * rows_pad * 32;
+    for (int w = threadIdx.x; w < C * 8; w += 256) {
+      const int c = w >> 3, unit = w & 7;
+      const int f = c * HW + hw;
+      float v[4], hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = s_act[(unit * 4 + e) * ld + c];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
+      const int rt = f / TN, rr = f - rt * TN;
+      const int64_t off = (((int64_t)kc * tiles + rt) * TN + rr) * 32 + ((unit ^ (rr & 7)) << 2);
+      *reinterpret_cast<float4*>(out + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(out + term_stride + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// zero rows [K, rows_pad) of the x^T image (the padding of the last row tile)
+__global__ void __launch_bounds__(256)
+k_pack_zero_rows(float* __restrict__ out, int row0, int rows_pad, int k_chunks, int tile_rows) {
+  const int tiles = rows_pad / tile_rows;
+  const int64_t term_stride = (int64_t)k_chunks * rows_pad * 32;
+  const int n_rows = rows_pad - row0;
+  const int64_t total = (int64_t)n_rows * k_chunks * 8;
+  for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < total; w += (int64_t)gridDim.x * 256) {
+    const int unit = (int)(w & 7);
+    const int64_t q = w >> 3;
+    const int kc = (int)(q / n_rows), f = row0 + (int)(q - (int64_t)kc * n_rows);
+    const int rt = f / tile_rows, rr = f - rt * tile_rows;
+    const int64_t off = (((int64_t)kc * tiles + rt) * tile_rows + rr) * 32 + ((unit ^ (rr & 7)) << 2);
+    *reinterpret_cast<float4*>(out + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(out + term_stride + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_unflatten_relu_mask(const float* __restrict__ gx, int64_t gx_ld, const float* __restrict__ y, int HW, int C,
+                      float* __restrict__ out) {
+  extern __shared__ float s_act[];          // gx row in f order: s[c*HW + hw]
+  const int b = blockIdx.x, K = C * HW;
+  for (int i = threadIdx.x; i < K; i += 256) s_act[i] = gx[(int64_t)b * gx_ld + i];
+  __syncthreads();
+  const float* yr = y + (int64_t)b * K;
+  float* o = out + (int64_t)b * K;
+  for (int i = threadIdx.x; i < K; i += 256) {      // i = hw*C + c (coalesced reads of y, writes of out)
+    const int hw = i / C, c = i - hw * C;
+    o[i] = (yr[i] > 0.0f) ? s_act[c * HW + hw] : 0.0f;
+  }
+}
+
 struct Params {
   const float* a;        // packed A image (tile_rows = 128)
   const float* b;        // packed B image (tile_rows = 256)
@@ -395,5 +503,53 @@ extern "C" int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed
     count_launch();
     B2RL_CHECK_LAUNCH();
   }
+  return B2RL_OK;
+}
+
+
+// flatten_NCHW(relu(y)) packed straight from the conv stack's NHWC output: act_3 + nn.Flatten of cfg/ape_x.json:37-51
+// (baseline/baseNetwork.py:204-209) folded into the heads' operand packing.  transpose = 0: A-role image of
+// x [B][C*HW] (forward); transpose = 1: B-role image of x^T (weight gradient of the heads).
+extern "C" int b2rl_gemm_pack_act_nhwc(const float* y_dev, int64_t B, int64_t HW, int64_t C, int32_t relu, int32_t transpose,
+                                       float* out_dev, void* stream) {
+  B2RL_REQUIRE(y_dev && out_dev, "null argument");
+  B2RL_REQUIRE(B >= 1 && HW >= 1 && C >= 1 && C * HW < (1 << 24) && B < (1 << 24), "bad shape");
+  B2RL_REQUIRE(((uintptr_t)out_dev % 16) == 0, "packed operand must be 16-byte aligned");
+  const int64_t K = C * HW;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!transpose) {
+    const int64_t rows_pad = (B + gemm::TM - 1) / gemm::TM * gemm::TM, kc = (K + gemm::KC - 1) / gemm::KC;
+    const size_t smem = (size_t)HW * (C + gemm::ACT_PAD) * sizeof(float);
+    B2RL_REQUIRE(smem <= 48 * 1024, "activation row too large for the staging tile");
+    gemm::k_pack_act_nhwc<false><<<(unsigned)rows_pad, 256, smem, st>>>(y_dev, (int)B, (int)HW, (int)C, relu, out_dev,
+                                                                       (int)rows_pad, (int)kc);
+    count_launch();
+  } else {
+    const int64_t rows_pad = (K + gemm::TN - 1) / gemm::TN * gemm::TN, kc = (B + gemm::KC - 1) / gemm::KC;
+    const size_t smem = (size_t)32 * (C + gemm::ACT_PAD) * sizeof(float);
+    B2RL_REQUIRE(smem <= 48 * 1024 && HW <= 65535, "activation tile too large");
+    gemm::k_pack_act_nhwc<true><<<dim3((unsigned)kc, (unsigned)HW), 256, smem, st>>>(y_dev, (int)B, (int)HW, (int)C, relu,
+                                                                                    out_dev, (int)rows_pad, (int)kc);
+    count_launch();
+    if (rows_pad > K) {
+      gemm::k_pack_zero_rows<<<64, 256, 0, st>>>(out_dev, (int)K, (int)rows_pad, (int)kc, gemm::TN);
+      count_launch();
+    }
+  }
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+// The backward counterpart: dL/dy (NHWC, [B][HW][C]) = dL/dx (NCHW-flatten order, [B][gx_ld]) permuted back and
+// masked by the ReLU (y > 0) — nn.Flatten's and act_3's backward in one launch.
+extern "C" int b2rl_unflatten_relu_mask(const float* gx_dev, int64_t gx_ld, const float* y_dev, int64_t B, int64_t HW,
+                                        int64_t C, float* out_dev, void* stream) {
+  B2RL_REQUIRE(gx_dev && y_dev && out_dev, "null argument");
+  B2RL_REQUIRE(B >= 1 && HW >= 1 && C >= 1 && gx_ld >= C * HW, "bad shape");
+  const size_t smem = (size_t)C * HW * sizeof(float);
+  B2RL_REQUIRE(smem <= 48 * 1024, "activation row too large for the staging tile");
+  gemm::k_unflatten_relu_mask<<<(unsigned)B, 256, smem, (cudaStream_t)stream>>>(gx_dev, gx_ld, y_dev, (int)HW, (int)C, out_dev);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
   return B2RL_OK;
 }

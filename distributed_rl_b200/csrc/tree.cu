@@ -516,7 +516,9 @@ __global__ void __launch_bounds__(1024)
 k_tree_top(const __grid_constant__ TreeView t, int k_first) {
   for (int k = k_first; k <= t.G; ++k) {
     const int64_t nk = (k == t.G) ? 1 : (t.cap2 >> (4 * k));
-    for (int64_t node = threadIdx.x; node < nk; node += blockDim.x) recompute_node<true>(t, k, node);
+    // plain (L1-cached) loads: level k_first-1 was written by an earlier launch, the levels above by this CTA
+    // itself before a __syncthreads — and no line of them was read earlier in this launch
+    for (int64_t node = threadIdx.x; node < nk; node += blockDim.x) recompute_node<false>(t, k, node);
     __syncthreads();
   }
 }
@@ -647,8 +649,8 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
   }
   // Large batch: leaves first, then the levels bottom-up.  A level with no more nodes than the batch has
   // entries is recomputed for ALL of its nodes (cheaper and contention-free: thousands of entries would
-  // otherwise recompute the same few nodes); everything from the first <= 4096-node level upwards is one
-  // single-CTA launch.
+  // otherwise recompute the same few nodes); everything from the first <= 256-node level upwards is one
+  // single-CTA launch (ncu: a 4096-node level in one CTA cost 30 of the 35 us).
   const unsigned g = grid_for(n, UPD_THREADS);
   int launches = 0;
   if (idx_dev) {
@@ -661,7 +663,10 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
   }
   const int64_t a0 = ring_start, b0 = (ring_start + n <= h->capacity) ? ring_start + n : h->capacity;
   const int64_t a1 = 0, b1 = (ring_start + n <= h->capacity) ? 0 : ring_start + n - h->capacity;
-  for (int k = 1; k < ks; ++k) {
+  // per-level launches while a level is wider than one CTA handles at a stroke (256 nodes), then one launch for the rest
+  int kt = 1;
+  while (kt < t.G && (t.cap2 >> (4 * kt)) > 256) ++kt;
+  for (int k = 1; k < kt; ++k) {
     const int64_t nk = t.cap2 >> (4 * k);
     if (idx_dev) {
       if (nk <= n) k_tree_level_all<<<grid_for(nk, 256), 256, 0, st>>>(t, k);
@@ -674,7 +679,7 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
     }
     ++launches;
   }
-  k_tree_top<<<1, 1024, 0, st>>>(t, ks);
+  k_tree_top<<<1, 256, 0, st>>>(t, kt);
   count_launch(launches + 1);
   B2RL_CHECK_LAUNCH();
   return publish_size_too ? publish_size(h, st) : B2RL_OK;
@@ -703,7 +708,7 @@ extern "C" int b2rl_tree_build(b2rl_replay* h, const float* prios_dev, int64_t n
     k_build_leaves<false><<<ctas, BUILD_THREADS, 0, st>>>(t, prios_dev, n, fused_upto, ticket);
   count_launch();
   if (ticket == nullptr) {
-    k_tree_top<<<1, 1024, 0, st>>>(t, fused_upto + 1);
+    k_tree_top<<<1, 256, 0, st>>>(t, fused_upto + 1);
     count_launch();
   }
   B2RL_CHECK_LAUNCH();

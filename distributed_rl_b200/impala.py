@@ -45,6 +45,7 @@ class ImpalaConfig:
     OPTIM_INFO: dict = field(default_factory=lambda: {"name": "rmsprop", "lr": 6e-4, "decay": 0})
     MODEL: dict = field(default_factory=default_impala_model)
     FUSED_CONV1: bool = True     # conv_1 (4 -> 16 channels) of every frame through libb2rl's tcgen05 kernel
+    DENSE_3XTF32: bool = True    # the 2592 -> 256 layer as a 3xTF32 tcgen05 GEMM (csrc/gemm.cu) instead of an fp32 SIMT sgemm
 
     @staticmethod
     def from_configuration():
@@ -137,6 +138,7 @@ class Learner:
         self.cfg = cfg or ImpalaConfig.from_configuration()
         self.device = torch.device(self.cfg.LEARNER_DEVICE)
         self.model = GraphAgent(self.cfg.MODEL).to(self.device)
+        self.model.dense_3xtf32 = bool(self.cfg.DENSE_3XTF32) and self.device.type == "cuda"
         self.mOptim = make_optimizer(self.cfg.OPTIM_INFO, self.model.getParameters())
         self._connect = connect
         self._memory = Replay(self.cfg, connect)

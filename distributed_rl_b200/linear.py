@@ -97,6 +97,16 @@ def split_pack(x: torch.Tensor, transpose: bool, b_role: bool) -> torch.Tensor:
     return out
 
 
+def pack_act_nhwc(y: torch.Tensor, transpose: bool) -> torch.Tensor:
+    """Operand image of flatten_NCHW(relu(y)) (transpose=False: A-role, [B][C*HW]) or of its transpose
+    (transpose=True: B-role) read straight from a channels_last (B, C, H, W) tensor — b2rl_gemm_pack_act_nhwc."""
+    B, C, H, W = y.shape
+    rows, k = (C * H * W, B) if transpose else (B, C * H * W)
+    out = torch.empty(_lib.load().b2rl_gemm_packed_floats(rows, k, int(transpose)), dtype=torch.float32, device=y.device)
+    _lib.check(_lib.load().b2rl_gemm_pack_act_nhwc(y.data_ptr(), B, H * W, C, 1, int(transpose), out.data_ptr(), _stream()))
+    return out
+
+
 def gemm_packed(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """C[M][N] = A[M][K] @ B[N][K]^T from packed operand images (A-role, B-role)."""
     if out is None:
@@ -175,6 +185,70 @@ class _Linear3x(torch.autograd.Function):
             else:
                 gws = wgrad()
         return (gx, None, *gws)
+
+
+class _ReluFlatLinear3x(torch.autograd.Function):
+    """h = flatten_NCHW(relu(y)) @ cat(ws, 0).T for a conv output `y` (B, C, H, W) stored channels_last, WITHOUT the
+    ReLU kernel, the NHWC -> NCHW flatten copy and their backward counterparts: the activation-side packs read y
+    coalesced, apply the ReLU, transpose through shared memory and write the operand images in the weights'
+    NCHW-flatten feature order (csrc/gemm.cu k_pack_act_nhwc); dL/dy comes back through one unflatten + ReLU-mask
+    kernel.  The weights' packs are the ordinary ones (shared with _Linear3x: cache keys "fwd" / "bwdT").
+    Same arithmetic as act_3 + nn.Flatten + _Linear3x (cfg/ape_x.json:37-71), operand for operand."""
+
+    @staticmethod
+    def forward(ctx, y, cache, *ws):
+        B, C, H, W = y.shape
+        N, K = sum(w.shape[0] for w in ws), C * H * W
+        b = cache.get("fwd") if cache is not None else None
+        if b is None:
+            b = _pack_pieces(ws, False, True)
+            if cache is not None:
+                cache["fwd"] = b
+        h = gemm_packed(pack_act_nhwc(y, False), b, B, N, K)
+        ctx.save_for_backward(y, *ws)
+        ctx.cache = cache
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        y, *ws = ctx.saved_tensors
+        B, C, H, W = y.shape
+        N, K = sum(w.shape[0] for w in ws), C * H * W
+        gh = gh.contiguous()
+        gy, gws = None, [None] * len(ws)
+        if ctx.needs_input_grad[0]:
+            bt = ctx.cache.get("bwdT") if ctx.cache is not None else None
+            gx = gemm_packed(split_pack(gh, False, False), bt if bt is not None else _pack_pieces(ws, True, True), B, K, N)
+            gy = torch.empty_like(y)                                         # channels_last like y
+            _lib.check(_lib.load().b2rl_unflatten_relu_mask(gx.data_ptr(), gx.stride(0), y.data_ptr(), B, H * W, C,
+                                                           gy.data_ptr(), _stream()))
+        if any(ctx.needs_input_grad[2:]):
+            def wgrad():
+                gw = gemm_packed(split_pack(gh, True, False), pack_act_nhwc(y, True), N, K, B)
+                return list(torch.split(gw, [w.shape[0] for w in ws], 0))
+            if WeightGradSink.usable(ws):
+                sink = _SINK
+
+                def deferred():
+                    for w, g in zip(ws, wgrad()):
+                        sink.accumulate(w, g)
+                sink.submit(deferred, keep=(gh, y))
+            else:
+                gws = wgrad()
+        return (gy, None, *gws)
+
+
+def relu_flat_linear3x(y: torch.Tensor, ws, cache: dict | None = None) -> torch.Tensor:
+    """See _ReluFlatLinear3x.  `y`: (B, C, H, W) fp32 CUDA, channels_last-contiguous, PRE-ReLU conv output."""
+    return _ReluFlatLinear3x.apply(y, cache, *ws)
+
+
+def relu_flat_supported(y: torch.Tensor, ws) -> bool:
+    return (y.is_cuda and y.dim() == 4 and y.dtype == torch.float32
+            and y.is_contiguous(memory_format=torch.channels_last)
+            and y.shape[2] * y.shape[3] * (y.shape[1] + 1) * 4 <= 48 * 1024
+            and all(w.dim() == 2 and w.shape[1] == y.shape[1] * y.shape[2] * y.shape[3] for w in ws)
+            and not any(w.shape[0] % 32 for w in ws[:-1]))
 
 
 def linear3x(x: torch.Tensor, w, cache: dict | None = None) -> torch.Tensor:

@@ -284,6 +284,16 @@ int b2rl_gemm_split_pack(const float* src_dev, int64_t src_rows, int64_t src_col
 int b2rl_gemm_split_pack_into(const float* src_dev, int64_t src_rows, int64_t src_cols, int64_t src_ld,
                               int32_t transpose, int32_t b_role, float* out_dev, int64_t total_rows,
                               int64_t total_k, int64_t row_offset, int64_t k_offset, void* stream);
+/* The two element-wise steps between the conv stack and the heads — the act_3 ReLU and nn.Flatten of
+ * cfg/ape_x.json:37-51 (baseline/baseNetwork.py:204-209) — folded into the heads' operand packing.  y_dev is the conv
+ * stack's output as it lies in memory (NHWC: [B][HW][C]); the images index features in the NCHW-flatten order
+ * f = c*HW + hw the reference's weights use.  transpose = 0: A-role image of x = relu(y) as [B][C*HW] (forward);
+ * transpose = 1: B-role image of x^T (the heads' weight gradient).  b2rl_unflatten_relu_mask is their backward:
+ * out[b][hw][c] = gx[b][c*HW + hw] * (y[b][hw][c] > 0). */
+int b2rl_gemm_pack_act_nhwc(const float* y_dev, int64_t B, int64_t HW, int64_t C, int32_t relu, int32_t transpose,
+                            float* out_dev, void* stream);
+int b2rl_unflatten_relu_mask(const float* gx_dev, int64_t gx_ld, const float* y_dev, int64_t B, int64_t HW, int64_t C,
+                             float* out_dev, void* stream);
 int64_t b2rl_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int64_t ldc);
 int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed_dev, float* c_dev, int64_t M,
                      int64_t N, int64_t K, int64_t ldc, float* workspace_dev, void* stream);

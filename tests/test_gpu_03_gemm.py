@@ -145,3 +145,27 @@ def test_graph_agent_fused_tail_equals_node_sequence():
     torch.testing.assert_close(outs[1], outs[0], rtol=1e-4, atol=1e-5)
     for a, b in zip(grads[1], grads[0]):
         torch.testing.assert_close(a, b, rtol=2e-3, atol=1e-4 * b.abs().max().item())
+
+
+def test_relu_flatten_folded_into_the_packs_matches_fp64(L):
+    """linear.relu_flat_linear3x: h = flatten_NCHW(relu(y)) @ W^T read straight from the conv stack's channels_last
+    output (ReLU applied while packing, the NHWC <-> NCHW feature permutation carried by the weight / x^T packs,
+    csrc/gemm.cu colmap) against act + nn.Flatten + matmul in fp64 — forward, dL/dy (with the ReLU mask) and dL/dW."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, C, H, W = 96, 64, 7, 7
+    y = torch.randn(B, C, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last).requires_grad_()
+    w1 = (torch.randn(512, C * H * W, device="cuda", generator=g) * 0.02).requires_grad_()
+    w2 = (torch.randn(512, C * H * W, device="cuda", generator=g) * 0.02).requires_grad_()
+    gh = torch.randn(B, 1024, device="cuda", generator=g)
+    assert L.relu_flat_supported(y, [w1, w2])
+    h = L.relu_flat_linear3x(y, [w1, w2])
+    h.backward(gh)
+    yd = y.detach().double().requires_grad_()
+    wd = torch.cat([w1, w2]).detach().double().requires_grad_()
+    href = torch.relu(yd).flatten(1) @ wd.T                      # nn.Flatten of the logical NCHW tensor
+    href.backward(gh.double())
+    assert _rel(h, href.detach()) < 5e-6
+    assert y.grad.shape == y.shape and y.grad.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(y.grad, yd.grad) < 5e-6
+    assert _rel(torch.cat([w1.grad, w2.grad]), wd.grad) < 5e-6
+    assert (y.grad[y.detach() <= 0] == 0).all()                  # ReLU mask applied
