@@ -16,6 +16,8 @@
 //   k_splitk_reduce sums the K-split partials in split order: the result is deterministic (no atomics)
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace b2rl {
 namespace gemm {
 
@@ -73,6 +75,49 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, N>>3 @17, M>>4 @24
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+
+// ---- cta_group::2 helpers (CTA pair: one 256-row MMA over two SMs) ---------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same CTA-relative address in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* b, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(sptr(b)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(sptr(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {   // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   sptr(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc),
+      "r"(idesc), "r"(accumulate) : "memory");
+}
+// M = 256 over the pair, N = 256
+constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+constexpr int STAGE2 = 2 * A_TILE + B_TILE;          // A hi+lo (my 128 rows) + my HALF of B hi+lo: 64 KiB
+constexpr int STAGES2 = 3;
 
 // ---- operand packing ---------------------------------------------------------
 // Image layout: [term 0=hi,1=lo][k_chunk][row_tile][row_in_tile][128 B, 16-byte units XOR (row & 7)]
@@ -364,6 +409,141 @@ k_gemm_tf32x3(const __grid_constant__ Params P) {
   }
 }
 
+
+// ---- the same GEMM on CTA pairs (tcgen05 cta_group::2) ------------------------------------------------------------
+// Two CTAs of a cluster own m-tiles 2c and 2c+1 of the same n-tile and K split.  The leader (rank 0) issues ONE
+// M = 256 MMA per step for both; A comes from each CTA's own shared memory (its 128 rows) and every CTA holds only
+// its HALF of the B tile (128 of the 256 rows), which the pair's tensor cores share.  Per SM and K chunk 64 KiB are
+// staged instead of 96 KiB, for the same MMA work per SM: the single-CTA kernel is bound by exactly that
+// (shared-memory fill + operand reads per SM; tensor pipe 49 % active), and the freed space buys a
+// third pipeline stage.  Barriers: every CTA's loader arms its LOCAL full barrier (tx bytes); a relay thread per CTA
+// forwards "my stage is full" to the leader's pair barrier (count 2, remote arrive); the leader's tcgen05.commit is
+// multicast to both CTAs' empty / accumulator barriers.
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_tf32x3_2cta(const __grid_constant__ Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (sptr(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full[STAGES2], pair_full[STAGES2], empty[STAGES2], acc_full;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int64_t mt = blockIdx.x, nt = blockIdx.y;     // blockIdx.x = 2 * pair + crank
+  const int64_t per = (P.k_chunks + P.splits - 1) / P.splits;
+  const int64_t k0 = (int64_t)blockIdx.z * per;
+  const int64_t k1 = (k0 + per < P.k_chunks) ? k0 + per : P.k_chunks;
+  const int64_t nk = k1 - k0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES2; ++i) { mbar_init(&full[i], 1); mbar_init(&pair_full[i], 2); mbar_init(&empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  cluster_sync_all();                 // both CTAs' barriers exist before anything can arrive at them
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&s_tmem)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  cluster_sync_all();                 // both halves of the pair's TMEM are allocated
+
+  if (nk > 0) {
+    const int64_t a_term = P.k_chunks * P.m_tiles * (TM * 32);
+    const int64_t b_term = P.k_chunks * P.n_tiles * (TN * 32);
+    if (warp == 0) {
+      if (lane == 0) {                // loader: my A tile + my half of the B tile
+        for (int64_t i = 0; i < nk; ++i) {
+          const int s = (int)(i % STAGES2);
+          mbar_wait(&empty[s], ((i / STAGES2) & 1) ^ 1);
+          const int64_t kc = k0 + i;
+          const float* a_hi = P.a + (kc * P.m_tiles + mt) * (TM * 32);
+          const float* b_hi = P.b + (kc * P.n_tiles + nt) * (TN * 32) + (int64_t)crank * ((TN / 2) * 32);
+          uint8_t* st = smem + (size_t)s * STAGE2;
+          mbar_expect_tx(&full[s], STAGE2);
+          bulk_g2s(st, a_hi, A_TILE, &full[s]);
+          bulk_g2s(st + A_TILE, a_hi + a_term, A_TILE, &full[s]);
+          bulk_g2s(st + 2 * A_TILE, b_hi, B_TILE / 2, &full[s]);
+          bulk_g2s(st + 2 * A_TILE + B_TILE / 2, b_hi + b_term, B_TILE / 2, &full[s]);
+        }
+      }
+    } else if (warp == 2) {
+      if (lane == 0) {                // relay: my stage landed -> tell the leader's pair barrier
+        for (int64_t i = 0; i < nk; ++i) {
+          const int s = (int)(i % STAGES2);
+          mbar_wait(&full[s], (i / STAGES2) & 1);
+          mbar_arrive_remote(&pair_full[s], 0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && crank == 0) {  // the leader issues the pair's MMAs
+        for (int64_t i = 0; i < nk; ++i) {
+          const int s = (int)(i % STAGES2);
+          mbar_wait_cluster(&pair_full[s], (i / STAGES2) & 1);
+          tc_fence_after();
+          const uint32_t base = sptr(smem + (size_t)s * STAGE2);
+          const uint32_t a_hi = base, a_lo = base + A_TILE, b_hi = base + 2 * A_TILE, b_lo = b_hi + B_TILE / 2;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t o = ks * 32;
+            tc_mma_tf32_2cta(tmem, make_desc(a_lo + o), make_desc(b_hi + o), IDESC2, (i | ks) ? 1u : 0u);   // small terms first
+            tc_mma_tf32_2cta(tmem, make_desc(a_hi + o), make_desc(b_lo + o), IDESC2, 1u);
+            tc_mma_tf32_2cta(tmem, make_desc(a_hi + o), make_desc(b_hi + o), IDESC2, 1u);
+          }
+          tc_commit2(&empty[s]);      // both CTAs' stage s may be refilled
+        }
+        tc_commit2(&acc_full);        // both CTAs' halves of the accumulator are complete
+      }
+    } else if (warp >= 3) {
+      // ------------------------------- epilogue (my 128 rows) -------------------------------
+      const int wq = warp & 3;
+      mbar_wait(&acc_full, 0);
+      tc_fence_after();
+      uint8_t* stg = smem + (size_t)wq * 4096;
+      const int64_t row0 = mt * TM + wq * 32;
+      const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16);
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        tc_ld16(tbase + c0, v0);
+        tc_ld16(tbase + c0 + 16, v1);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+              make_uint4(v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) =
+              make_uint4(v1[4 * g], v1[4 * g + 1], v1[4 * g + 2], v1[4 * g + 3]);
+        }
+        __syncwarp();
+        const int64_t col0 = nt * TN + c0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int off = (i * 32 + lane) * 16;
+          const int row = off >> 7, unit = (off >> 4) & 7;
+          const int64_t m = row0 + row, n = col0 + unit * 4;
+          float* dst = P.c + ((int64_t)blockIdx.z * P.M + m) * P.ldc + n;
+          if (m < P.M && n + 3 < P.N) {
+            *reinterpret_cast<float4*>(dst) =
+                *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+          } else if (m < P.M && n < P.N) {
+            const float* x = reinterpret_cast<const float*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+            for (int e = 0; e < 4 && n + e < P.N; ++e) dst[e] = x[e];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // neither CTA frees TMEM / exits while the pair may still use it
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  }
+}
+
 // C[i] = sum over splits (in split order: deterministic) of partial[z][i]; one thread per 4 columns
 __global__ void __launch_bounds__(256)
 k_splitk_reduce(const float* __restrict__ partial, int splits, int64_t M, int64_t N, int64_t ldc, float* __restrict__ c) {
@@ -477,9 +657,16 @@ extern "C" int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed
   B2RL_CUDA(cudaGetDevice(&dev));
   static bool attr[64] = {false};
   const size_t smem_bytes = (size_t)gemm::STAGES * gemm::STAGE + 1024;
+  const size_t smem_bytes2 = (size_t)gemm::STAGES2 * gemm::STAGE2 + 1024;
   if (!attr[dev & 63]) {
     B2RL_CUDA(cudaFuncSetAttribute(gemm::k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    B2RL_CUDA(cudaFuncSetAttribute(gemm::k_gemm_tf32x3_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes2));
     attr[dev & 63] = true;
+  }
+  static int use_2cta = -1;
+  if (use_2cta < 0) {
+    const char* e = getenv("B2RL_GEMM_2CTA");     // opt-in: measured 23.5 us vs 21.5 us for the single-CTA kernel on the
+    use_2cta = (e && e[0] == '1') ? 1 : 0;        // heads' shapes (the GEMM is overhead-bound there)
   }
   const int64_t splits = gemm_splits(M, N, K, sms);
   B2RL_REQUIRE(splits == 1 || (workspace_dev && ((uintptr_t)workspace_dev % 16) == 0),
@@ -494,7 +681,17 @@ extern "C" int b2rl_gemm_tf32x3(const float* a_packed_dev, const float* b_packed
   P.splits = (int32_t)splits;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)P.m_tiles, (unsigned)P.n_tiles, (unsigned)splits);
-  gemm::k_gemm_tf32x3<<<grid, gemm::THREADS, smem_bytes, st>>>(P);
+  if (use_2cta && (P.m_tiles % 2) == 0) {       // CTA pairs along M (tcgen05 cta_group::2)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(gemm::THREADS); cfg.dynamicSmemBytes = smem_bytes2; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    B2RL_CUDA(cudaLaunchKernelEx(&cfg, gemm::k_gemm_tf32x3_2cta, P));
+  } else {
+    gemm::k_gemm_tf32x3<<<grid, gemm::THREADS, smem_bytes, st>>>(P);
+  }
   count_launch();
   B2RL_CHECK_LAUNCH();
   if (splits > 1) {
