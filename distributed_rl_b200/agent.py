@@ -38,9 +38,10 @@ class _ConvSplitBackward(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, stride, padding):
+        from .linear import taped
         ctx.save_for_backward(x, w)
         ctx.sp = (tuple(stride), tuple(padding))
-        return torch.nn.functional.conv2d(x, w, None, stride, padding)
+        return taped(lambda: torch.nn.functional.conv2d(x, w, None, stride, padding))
 
     @staticmethod
     def backward(ctx, gy):
@@ -85,9 +86,14 @@ class ConvStack(nn.Sequential):
     split_backward = False     # route Conv2d layers through _ConvSplitBackward (set by the learner)
 
     def _run(self, layer, x):
-        if self.split_backward and isinstance(layer, nn.Conv2d) and x.is_cuda and torch.is_grad_enabled() \
+        from . import linear as _lin
+        taping = _lin._TAPE is not None
+        if (self.split_backward or taping) and isinstance(layer, nn.Conv2d) and x.is_cuda \
+                and (torch.is_grad_enabled() or taping) \
                 and layer.bias is None and layer.dilation == (1, 1) and layer.groups == 1:
             return _ConvSplitBackward.apply(x, layer.weight, layer.stride, layer.padding)
+        if taping and isinstance(layer, nn.ReLU):
+            return _lin._ReluTaped.apply(x)
         return layer(x)
 
     def forward(self, xs):

@@ -58,6 +58,7 @@ class ApexConfig:
     PARALLEL_FORWARDS: bool = True   # the three forward passes of a step on three streams (fork/join inside the graph)
     FUSED_DUELING_TAIL: bool = True  # heads' second layers + dueling combine in one kernel (csrc/dueling.cu)
     DENSE_3XTF32: bool = True       # dense heads as 3xTF32 tcgen05 GEMMs at fp32 accuracy (csrc/gemm.cu)
+    BATCHED_ONLINE: bool = True     # the online net's two passes (s with grad, s' without) as ONE B = 2*BATCHSIZE call
 
     @staticmethod
     def from_configuration():
@@ -475,7 +476,46 @@ class Learner:
         else:
             torch.cuda.current_stream(self.device).wait_event(packs_done)
         with self.model.packed_heads_cache():     # the online weights are packed once for both passes
-            if self.cfg.PARALLEL_FORWARDS:
+            if self.cfg.PARALLEL_FORWARDS and self.cfg.BATCHED_ONLINE:
+                # Q(s) (with grad) and Q_online(s') (without) share the online weights: every kernel after conv_1 is
+                # launch / set-up bound at B = 512, so both run as ONE B = 2*BATCHSIZE pass
+                # (conv_2, conv_3, heads' GEMM, dueling tail: one launch each instead of two).  The pass is recorded
+                # on an OutputTape; the autograd graph of the s half is then built by replaying the recorded per-op
+                # outputs (first B rows: views, no kernels) through the same forward code.  Q_target(s') runs
+                # beside it on a second stream.
+                from .linear import OutputTape
+                s1, s2, e0, e1, e2 = self._streams()
+                cur = torch.cuda.current_stream(self.device)
+                self.model.prepack_heads()
+                B = idx.numel()
+                c_out = self._pack1.c_out
+                if getattr(self, "_y_big", None) is None or self._y_big.shape[1] != B:
+                    self._y_big = torch.empty((3, B, 20, 20, c_out), dtype=torch.float32, device=self.device)
+                big = self._y_big          # [0] conv_1(s) online, [1] conv_1(s') online, [2] conv_1(s') target
+                with torch.no_grad():
+                    R.conv1_fused(st.field_view("state"), idx, self._pack1, relu=True, out=big[0:1])
+                    y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True, out=big[1:3])[1]
+                e0.record(cur)
+                s1.wait_event(e0)
+                s2.wait_event(e0)
+                with torch.no_grad():
+                    with torch.cuda.stream(s2):
+                        qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
+                        e2.record(s2)
+                    with torch.cuda.stream(s1):
+                        self.model.prepack_heads(transposed=True)   # W^T operand of the heads' dgrad, off the main branch
+                        e1.record(s1)
+                    y_both = big[0:2].view(2 * B, 20, 20, c_out).permute(0, 3, 1, 2)     # logical NCHW, physical NHWC
+                    with OutputTape.record() as tape:
+                        q_all = self.model.forward_from_conv1(y_both, True)[0]          # :78 and :87 in one pass
+                qn_online = q_all[B:]
+                y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st,
+                                         big[0].permute(0, 3, 1, 2), True)
+                with OutputTape.replay(tape.half(B)):
+                    q = self.model.forward_from_conv1(y, True)[0]                       # graph only: outputs replayed
+                cur.wait_event(e1)
+                cur.wait_event(e2)
+            elif self.cfg.PARALLEL_FORWARDS:
                 # The three passes are independent until the target kernel: fork them onto three streams
                 # (captured as parallel branches of the step's CUDA graph) so their small kernels overlap.
                 s1, s2, e0, e1, e2 = self._streams()

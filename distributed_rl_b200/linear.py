@@ -83,6 +83,75 @@ class _SinkContext:
 _SINK: WeightGradSink | None = None
 
 
+class OutputTape:
+    """Record the outputs of the network's custom ops during one (no-grad) pass, or replay recorded outputs instead
+    of recomputing them while a second pass only BUILDS the autograd graph.
+
+    Use: the online network's two passes of an Ape-X step (Q(s) with grad, Q(s') without) run as ONE batched call
+    under `OutputTape.record()`; the per-op outputs of the s half (`tape.half(n)`: views of the first n rows) are then
+    replayed under `OutputTape.replay(...)` while `forward_from_conv1(y_s)` is called again with grad enabled: every
+    op returns its recorded output (no kernel launch) and registers its normal backward.  The ops consult the tape in
+    execution order: conv_2, act_2, conv_3, heads (ReLU + Flatten + first layers), dueling tail."""
+
+    def __init__(self, mode, outs=None):
+        self.mode, self.outs, self.pos = mode, ([] if outs is None else list(outs)), 0
+
+    @staticmethod
+    def record():
+        return OutputTape("record")
+
+    @staticmethod
+    def replay(outs):
+        return OutputTape("replay", outs)
+
+    def half(self, n):
+        return [t[:n] for t in self.outs]
+
+    def __enter__(self):
+        global _TAPE
+        self._old, _TAPE = _TAPE, self
+        return self
+
+    def __exit__(self, *exc):
+        global _TAPE
+        _TAPE = self._old
+        if self.mode == "replay" and exc[0] is None:
+            assert self.pos == len(self.outs), "the replayed pass ran fewer ops than were recorded"
+        return False
+
+
+_TAPE: OutputTape | None = None
+
+
+def taped(compute):
+    """Output of one op: computed (and recorded) or taken from the tape."""
+    t = _TAPE
+    if t is None:
+        return compute()
+    if t.mode == "record":
+        out = compute()
+        t.outs.append(out)
+        return out
+    out = t.outs[t.pos]
+    t.pos += 1
+    return out
+
+
+class _ReluTaped(torch.autograd.Function):
+    """nn.ReLU whose output can come from the tape (backward: the usual mask on the output)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = taped(lambda: torch.relu(x))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return torch.ops.aten.threshold_backward(gy, y, 0)
+
+
 def split_pack(x: torch.Tensor, transpose: bool, b_role: bool) -> torch.Tensor:
     """{hi, lo} TF32 operand image of a 2-D fp32 CUDA matrix (or of its transpose)."""
     if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda:
@@ -204,7 +273,7 @@ class _ReluFlatLinear3x(torch.autograd.Function):
             b = _pack_pieces(ws, False, True)
             if cache is not None:
                 cache["fwd"] = b
-        h = gemm_packed(pack_act_nhwc(y, False), b, B, N, K)
+        h = taped(lambda: gemm_packed(pack_act_nhwc(y, False), b, B, N, K))
         ctx.save_for_backward(y, *ws)
         ctx.cache = cache
         return h
@@ -268,9 +337,13 @@ class _DuelingTail(torch.autograd.Function):
     def forward(ctx, h, wa, wv):
         M, H2 = h.shape
         A, H = wa.shape
-        q = torch.empty(M, A, dtype=torch.float32, device=h.device)
-        _lib.check(_lib.load().b2rl_dueling_forward(h.data_ptr(), M, H, wa.data_ptr(), A, wv.data_ptr(), q.data_ptr(),
-                                                    _stream()))
+
+        def compute():
+            q = torch.empty(M, A, dtype=torch.float32, device=h.device)
+            _lib.check(_lib.load().b2rl_dueling_forward(h.data_ptr(), M, H, wa.data_ptr(), A, wv.data_ptr(), q.data_ptr(),
+                                                        _stream()))
+            return q
+        q = taped(compute)
         ctx.save_for_backward(h, wa, wv)
         return q
 

@@ -225,9 +225,9 @@ def test_impala_learner_train_matches_oracle():
     assert all(torch.isfinite(p).all().item() for p in L.model.parameters())
 
 
-def _first_step_gradients(apex, fused, B=64, N=8192):
+def _first_step_gradients(apex, fused, B=64, N=8192, **kw):
     """Gradients (before the optimizer) of one Ape-X step on the slots the device RNG draws."""
-    cfg, L = _mk(apex, B=B, N=N, seed=11, FUSED_CONV1=fused)
+    cfg, L = _mk(apex, B=B, N=N, seed=11, FUSED_CONV1=fused, **kw)
     _fill(L, N, seed=5)
     st = L.memory.store
     idx, _, w = st.sample(B, beta=cfg.BETA, want_prob=False)
@@ -257,6 +257,20 @@ def test_fused_conv1_gradients_equal_staged_gradients(apex):
     names = [n for n, _ in L0.model.named_parameters()]
     for n, a, b in zip(names, g1, g0):
         assert b.abs().max() > 0, n
+        r = _rel(a, b)
+        assert r <= 2e-5, (n, r)
+
+
+def test_batched_online_pass_equals_separate_passes(apex):
+    """BATCHED_ONLINE: Q(s) and Q_online(s') as ONE B = 2*BATCHSIZE pass recorded on an OutputTape, the autograd graph
+    of the s half built by replaying the recorded outputs — against the three separate passes: same TD errors and
+    priorities, every gradient equal norm-wise (cuDNN may pick another algorithm at the doubled batch: 2e-5)."""
+    L0, i0, o0, g0 = _first_step_gradients(apex, True, BATCHED_ONLINE=False)
+    L1, i1, o1, g1 = _first_step_gradients(apex, True, BATCHED_ONLINE=True)
+    assert torch.equal(i0, i1)
+    np.testing.assert_allclose(o1["td"].cpu().numpy(), o0["td"].cpu().numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(o1["prio"].cpu().numpy(), o0["prio"].cpu().numpy(), rtol=1e-4, atol=1e-6)
+    for n, a, b in zip([n for n, _ in L0.model.named_parameters()], g1, g0):
         r = _rel(a, b)
         assert r <= 2e-5, (n, r)
 
