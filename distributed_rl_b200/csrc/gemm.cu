@@ -198,12 +198,15 @@ k_pack_act_nhwc(const float* __restrict__ y, int B, int HW, int C, int relu, flo
     // one CTA per image row b (rows >= B are zero padding): s[hw][c], row stride C + 1
     const int b = blockIdx.x;
     const int ld = C + ACT_PAD;
+    const uint32_t magic_c = (uint32_t)((0x100000000ull + C - 1) / C);      // i / C == (i * magic) >> 32 for i < 2^24
+    const uint32_t magic_hw = (uint32_t)((0x100000000ull + HW - 1) / HW);
     if (b < B) {
       const float* src = y + (int64_t)b * K;
       for (int i = threadIdx.x; i < K; i += 256) {
         float v = src[i];
         if (relu) v = fmaxf(v, 0.0f);
-        s_act[(i / C) * ld + (i % C)] = v;
+        const int hw = (int)__umulhi((uint32_t)i, magic_c);
+        s_act[hw * ld + (i - hw * C)] = v;
       }
     }
     __syncthreads();
@@ -211,11 +214,13 @@ k_pack_act_nhwc(const float* __restrict__ y, int B, int HW, int C, int relu, flo
     const int64_t term_stride = (int64_t)k_chunks * rows_pad * 32;
     for (int w = threadIdx.x; w < k_chunks * 8; w += 256) {
       const int kc = w >> 3, unit = w & 7;
+      const int f0 = kc * KC + unit * 4;
+      int c = (int)__umulhi((uint32_t)f0, magic_hw), hw = f0 - c * HW;      // f = c*HW + hw, walked incrementally
       float v[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int f = kc * KC + unit * 4 + e;
-        v[e] = (b < B && f < K) ? s_act[(f % HW) * ld + (f / HW)] : 0.0f;
+        v[e] = (b < B && f0 + e < K) ? s_act[hw * ld + c] : 0.0f;
+        if (++hw == HW) { hw = 0; ++c; }
       }
       float hi[4], lo[4];
 #pragma unroll

@@ -615,7 +615,7 @@ int b2rl_tree_update_impl(b2rl_replay* h, const int64_t* idx_dev, int64_t ring_s
   // first stored level that fits the small kernel's shared memory / the single-CTA top kernel
   int ks = 1;
   while (ks < t.G && (t.cap2 >> (4 * ks)) > US_SMEM_NODES) ++ks;
-  if (!force_large && n <= 2 * US_THREADS) {
+  if (!force_large && n <= US_THREADS) {      // (two chunked launches cost 21 us, the large path 14 us)
     static long long* probe = nullptr;
     static bool attr_set = false;
     if (!attr_set) {

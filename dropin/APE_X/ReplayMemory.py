@@ -21,4 +21,14 @@ class Replay(_Replay):
         super().__init__(cfg, connect=_connect(cfg.REDIS_SERVER))
 
 
-Replay_Server = Replay   # the out-of-process variant (:170-257) is out of scope; same surface
+from distributed_rl_b200.replay_server import Replay_Server as _ReplayServerClient
+
+
+class Replay_Server(_ReplayServerClient):
+    """Consumer of a stand-alone ReplayServer (:170-257)."""
+
+    def __init__(self):
+        import configuration as C
+        cfg = ApexConfig.from_configuration()
+        super().__init__(cfg, connect=_connect(cfg.REDIS_SERVER),
+                         connect_push=_connect(getattr(C, "REDIS_SERVER_PUSH", cfg.REDIS_SERVER)))

@@ -179,3 +179,54 @@ def test_apex_run_loop_control_plane(tmp_path):
     assert L.memory.lock is False
     assert set(torch.load(os.path.join(cfg.LOG_W, "weight.pth"))) == set(L.model.state_dict())
     assert pickle.loads(conn.get("count")) in (1, 0)
+
+
+def test_standalone_replay_server_round_trip():
+    """ReplayServer (APE_X/ReplayServer.py) serving pickled minibatches over the reference's Redis keys,
+    Replay_Server (APE_X/ReplayMemory.py:170-257) consuming them, priorities flowing back through `update`,
+    FLAG_BATCH / FLAG_ENOUGH / FLAG_REMOVE honoured — one process, two connections' worth of keys in one stand-in."""
+    from distributed_rl_b200 import apex
+    from distributed_rl_b200.replay_server import ReplayServer, Replay_Server
+    conn = FakeRedis()
+    cfg = apex.ApexConfig(BATCHSIZE=4, REPLAY_MEMORY_LEN=64, BUFFER_SIZE=8, LEARNER_DEVICE="cuda:0")
+    srv = ReplayServer(cfg, conn, conn, m=3)
+    cli = Replay_Server(cfg, conn, conn)
+    assert pickle.loads(conn.get("FLAG_BATCH")) is False
+    rng = np.random.default_rng(0)
+    recs = [_apex_rec(rng, 0.5 + 0.01 * i) for i in range(20)]
+    for r in recs[:6]:
+        conn.rpush("experience", pickle.dumps(r))
+    st = srv.serve_once()
+    assert st["ingested"] == 6 and st["batches_queued"] == 0 and conn.llen("BATCH") == 0    # below BUFFER_SIZE
+    for r in recs[6:]:
+        conn.rpush("experience", pickle.dumps(r))
+    st = srv.serve_once()
+    assert st["ingested"] == 14 and conn.llen("BATCH") == 3
+    st = srv.serve_once()
+    assert pickle.loads(conn.get("FLAG_BATCH")) is True
+    cli.poll_once()
+    assert conn.llen("BATCH") == 0 and len(cli.deque) == 3 and pickle.loads(conn.get("FLAG_ENOUGH")) is False
+    batch = cli.sample()
+    s, a, r, ns, d, w, idx = batch
+    assert s.shape == (4, 4, 84, 84) and ns.shape == (4, 4, 84, 84) and len(a) == 4 and w.shape == (4,)
+    ii = idx.numpy()
+    np.testing.assert_array_equal(s, np.stack([recs[i][0] for i in ii]))           # the served rows are the records
+    np.testing.assert_array_equal(a, [recs[i][1] for i in ii])
+    # a learner can train on it as is (host arrays, reference signature) and send priorities back
+    L = apex.Learner(cfg, connect=None, start_replay=False)
+    info, prio, idx2, _ = L.train(batch)
+    cli.update(list(idx2), prio.cpu().numpy())
+    cli.idx += [0] * 1000; cli.vals.append(np.full(1000, 0.25, np.float32))         # force the > 1000 flush
+    cli.poll_once()
+    assert conn.llen("update") == 1
+    assert srv.serve_once()["updates_applied"] == 1004
+    torch.cuda.synchronize()
+    pr = srv.store.priorities(0, 20).cpu().numpy()
+    assert pr[0] == np.float32(0.25)
+    for i, p in zip(idx2.numpy()[::-1], prio.cpu().numpy()[::-1]):
+        if i != 0:
+            assert pr[i] == p
+            break
+    assert cli.sample() is not False and cli.sample() is not False and cli.sample() is False
+    cli.lock = True; cli.poll_once()
+    assert pickle.loads(conn.get("FLAG_REMOVE")) is True
