@@ -644,24 +644,35 @@ def main():
     if cfg.DENSE_3XTF32:
         # the dominant kernel by device time: the 3xTF32 GEMM of the fused 3136 -> 2x512 heads (forward shape)
         from distributed_rl_b200 import linear as LIN
-        Mg, Ng, Kg = B, 1024, 3136
-        xa = LIN.split_pack(torch.randn(Mg, Kg, device=dev), False, False)
-        wb = LIN.split_pack(torch.randn(Ng, Kg, device=dev) * 0.02, False, True)
-        og = torch.empty(Mg, Ng, device=dev)
-        g_us = time_graph(lambda ix: LIN.gemm_packed(xa, wb, Mg, Ng, Kg, out=og))
+        # the forward call of the step: the online network's two passes run as ONE M = 2B GEMM (BATCHED_ONLINE)
+        batched = bool(cfg.BATCHED_ONLINE and cfg.PARALLEL_FORWARDS and cfg.FUSED_CONV1)
         tpeak = float(peaks.get("bf16_tflops", 1719.3))
-        alg_fl = 2.0 * Mg * Ng * Kg
-        t_ach = alg_fl / (g_us * 1e-6) / 1e12
+
+        def time_gemm(Mg, Ng, Kg):
+            xa = LIN.split_pack(torch.randn(Mg, Kg, device=dev), False, False)
+            wb = LIN.split_pack(torch.randn(Ng, Kg, device=dev) * 0.02, False, True)
+            og = torch.empty(Mg, Ng, device=dev)
+            us = time_graph(lambda ix: LIN.gemm_packed(xa, wb, Mg, Ng, Kg, out=og))
+            fl = 2.0 * Mg * Ng * Kg
+            return us, fl, fl / (us * 1e-6) / 1e12
+
+        Mg, Ng, Kg = (2 * B if batched else B), 1024, 3136
+        g_us, alg_fl, t_ach = time_gemm(Mg, Ng, Kg)
         kernels["k_gemm_tf32x3"] = {"launch_us": g_us, "algorithmic_flops_per_launch": alg_fl, "achieved_TFLOPs": t_ach,
                                     "frac": t_ach / tpeak, "tf32_TFLOPs_executed": 3 * t_ach,
-                                    "frac_of_tf32_peak_est": 3 * t_ach / (tpeak / 2),
-                                    "note": "launch_us covers k_gemm_tf32x3 + k_splitk_reduce for x[512x3136] @ W[1024x3136]^T; "
-                                            "algorithmic flops = the fp32 GEMM (2MNK); the kernel executes 3 TF32 products per "
-                                            "term pair, and TF32 dense peak is half the measured bf16 peak"}
+                                    "frac_of_tf32_peak_est": 3 * t_ach / (tpeak / 2), "shape_MNK": [Mg, Ng, Kg],
+                                    "note": f"launch_us covers k_gemm_tf32x3 + k_splitk_reduce for x[{Mg}x{Kg}] @ W[{Ng}x{Kg}]^T "
+                                            "(the step's forward call: Q(s) and Q_online(s') batched); algorithmic flops = the "
+                                            "fp32 GEMM (2MNK); the kernel executes 3 TF32 products per term pair, and TF32 dense "
+                                            "peak is half the measured bf16 peak"}
+        if batched:
+            u1, f1, a1 = time_gemm(B, Ng, Kg)
+            kernels["k_gemm_tf32x3(M=B, target-net call)"] = {"launch_us": u1, "algorithmic_flops_per_launch": f1,
+                                                              "achieved_TFLOPs": a1, "frac": a1 / tpeak, "shape_MNK": [B, Ng, Kg]}
         roofline = {"kernel": "k_gemm_tf32x3 — fp32-accurate dense heads as 3xTF32 tcgen05 GEMM (largest share of the step)",
                     "bound": "tensor", "achieved": t_ach, "peak": tpeak, "unit": "TFLOP/s", "frac": t_ach / tpeak,
                     "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1719.3",
-                    "traffic": None, "launch_us": g_us, "algorithmic_flops_per_launch": alg_fl,
+                    "traffic": None, "launch_us": g_us, "algorithmic_flops_per_launch": alg_fl, "shape_MNK": [Mg, Ng, Kg],
                     "note": "achieved counts the fp32 GEMM's 2MNK flops once; the tensor pipe executes 3x that in TF32 "
                             "(tf32_TFLOPs_executed), whose dense peak is bf16/2 — see kernels[k_gemm_tf32x3]"}
     # ---- the sum-tree kernels (the kernels north_star sets the HBM target on), SURVEY.md §8d bytes:
