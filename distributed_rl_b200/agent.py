@@ -54,14 +54,16 @@ class _ConvSplitBackward(torch.autograd.Function):
         def run(mask):
             return bw(gy, x, w, None, stride, padding, (1, 1), False, (0, 0), 1, mask)
 
-        gx = run((True, False, False))[0] if ctx.needs_input_grad[0] else None
+        # the weight gradient is handed to the sink BEFORE dL/dx is launched: its lane forks from the stream as it is
+        # now (gy complete) and runs beside this layer's own dgrad instead of behind it
         gw = None
         if ctx.needs_input_grad[1]:
             if WeightGradSink.usable((w,)):
                 sink = _lin._SINK
-                sink.submit(lambda: sink.accumulate(w, run((False, True, False))[1]), keep=(gy, x))
+                sink.submit(lambda: sink.accumulate(w, run((False, True, False))[1]), keep=(gy, x), lane=1)
             else:
                 gw = run((False, True, False))[1]
+        gx = run((True, False, False))[0] if ctx.needs_input_grad[0] else None
         return gx, gw, None, None
 
 

@@ -53,6 +53,7 @@ class ApexConfig:
     CHANNELS_LAST: bool = True      # NHWC activations/weights: cuDNN's TF32 kernels skip their layout transposes
     FUSED_CONV1: bool = True        # gather + conv_1 on the tcgen05 tensor cores (csrc/conv1.cu) in fused_step
     FUSED_OPTIM: bool = True        # RMSprop + zero_grad + grad-norm in one launch (csrc/optim.cu)
+    EARLY_HEAD_UPDATE: bool = True  # RMSprop of the dense heads as soon as their gradients are final (no clipping in :123-138)
     CUDNN_BENCHMARK: bool = True    # let cuDNN time its conv_2/conv_3 algorithms once (no precision change)
     DEFERRED_WGRAD: bool = True      # weight gradients on a side stream, off the critical path of backward
     PARALLEL_FORWARDS: bool = True   # the three forward passes of a step on three streams (fork/join inside the graph)
@@ -363,6 +364,14 @@ class Learner:
         if self.cfg.CHANNELS_LAST:
             self.model.to(memory_format=torch.channels_last)
             self.target_model.to(memory_format=torch.channels_last)
+            if self.cfg.FUSED_CONV1:
+                # conv_1 runs in libb2rl's kernels, which take the plain (c_out, 4, 8, 8) layout: keeping that weight
+                # channels_last cost one re-layout copy per pack (three launches per step)
+                for m in (self.model, self.target_model):
+                    name = m.first_conv_node()
+                    if name is not None and getattr(m, name).is_atari_conv1():
+                        w = getattr(m, name).conv_1.weight
+                        w.data = w.data.contiguous(memory_format=torch.contiguous_format)
         self.model.dense_3xtf32 = self.target_model.dense_3xtf32 = bool(self.cfg.DENSE_3XTF32)
         self.model.fused_dueling_tail = self.target_model.fused_dueling_tail = bool(self.cfg.FUSED_DUELING_TAIL)
 
@@ -442,6 +451,7 @@ class Learner:
             self._fork = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device),
                           torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event())
             self._ev_pk, self._ev_tg, self._ev_upd = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            self._ev_hp = torch.cuda.Event()
         return self._fork
 
     def _pack_conv1(self):
@@ -454,21 +464,34 @@ class Learner:
     def _pack_conv1_async(self):
         """The conv_1 weight packs of this step on a side stream (they only depend on the weights): they overlap
         the tree sample + scalar gather at the start of the step.  Returns the event the conv_1 launch waits for."""
-        s1 = self._streams()[0]
+        s1, s2 = self._streams()[:2]
         cur = torch.cuda.current_stream(self.device)
         self._ev_pk.record(cur)
         s1.wait_event(self._ev_pk)
+        s2.wait_event(self._ev_pk)
         with torch.cuda.stream(s1):
             self._pack_conv1()
             self._ev_pk.record(s1)
+        # The heads' forward operand (two 3136 x 512 matrices -> one packed image) is needed ~150 us into the step:
+        # built on the second side stream now instead of on the main branch in front of conv_1.
+        self._head_packs = None
+        if self.cfg.PARALLEL_FORWARDS and self.cfg.BATCHED_ONLINE:
+            with torch.cuda.stream(s2):
+                with self.model.packed_heads_cache():
+                    self.model.prepack_heads()
+                    self._head_packs = dict(self.model._pack_cache)
+                self._ev_hp.record(s2)
         return self._ev_pk
 
-    def _forward_backward_fused(self, idx, action, reward, done, weight, packs_done=None, update_tree=False):
+    def _forward_backward_fused(self, idx, action, reward, done, weight, packs_done=None, update_tree=False,
+                                early_update=False):
         """Same maths as _forward_backward, but s and s' are never staged as uint8/fp32 batches:
         conv_1 reads the sampled rows straight from the replay payload (b2rl_conv1_fused).
         `packs_done`: event after which the conv_1 weight packs are valid (None: pack here).
         `update_tree`: write the new priorities back on a side stream as soon as the target kernel has produced
-        them (overlapping backward); the caller then waits for `self._ev_upd` instead of calling store.update."""
+        them (overlapping backward); the caller then waits for `self._ev_upd` instead of calling store.update.
+        `early_update`: the caller WILL call self.step() next; the heads' part of that optimizer step may then be
+        issued here, behind their weight gradients on the sink's lane, while the conv stack's backward still runs."""
         st = self.memory.store
         w_on = getattr(self.model, self._conv_name).conv_1.weight
         if packs_done is None:
@@ -486,7 +509,11 @@ class Learner:
                 from .linear import OutputTape
                 s1, s2, e0, e1, e2 = self._streams()
                 cur = torch.cuda.current_stream(self.device)
-                self.model.prepack_heads()
+                early_packs = packs_done is not None and bool(getattr(self, "_head_packs", None))
+                if early_packs:
+                    self.model._pack_cache.update(self._head_packs)       # built on s2 at the start of the step
+                else:
+                    self.model.prepack_heads()
                 B = idx.numel()
                 c_out = self._pack1.c_out
                 if getattr(self, "_y_big", None) is None or self._y_big.shape[1] != B:
@@ -495,6 +522,8 @@ class Learner:
                 with torch.no_grad():
                     R.conv1_fused(st.field_view("state"), idx, self._pack1, relu=True, out=big[0:1])
                     y_tg = R.conv1_fused(st.field_view("next_state"), idx, self._pack2, relu=True, out=big[1:3])[1]
+                if early_packs:
+                    cur.wait_event(self._ev_hp)      # long done; the heads' GEMM is ~100 us away
                 e0.record(cur)
                 s1.wait_event(e0)
                 s2.wait_event(e0)
@@ -563,8 +592,17 @@ class Learner:
                 getattr(self.model, self._conv_name).split_backward = True
                 if self._world > 1:
                     self._bucket.attach_sink(self._sink)
+                # Learner.step (:123-138) has no clipping: a parameter can be stepped once its own gradient is final.
+                # At world size 1 the heads (97 % of the elements) are final ~150 us before the conv stack's.
+                self._early_params = [p for n, p in self.model.named_parameters()
+                                      if not n.startswith(self._conv_name + ".")]
+                self._early_ok = (self._world == 1 and self.cfg.EARLY_HEAD_UPDATE and bool(self._early_params)
+                                  and self.optim.set_early(self._early_params))
             with self._sink.active():
                 q.backward(out["grad_q"])
+            if early_update and self._early_ok and \
+                    all(id(p) in self._sink.accumulated[0] for p in self._early_params):
+                self._sink.run_on_lane(self.optim.step_early, 0)
             self._sink.join()
         else:
             q.backward(out["grad_q"])
@@ -608,7 +646,7 @@ class Learner:
                                 max_w=max_w)
                 idx = c["idx"]
                 out = self._forward_backward_fused(idx, c["action"].to(torch.int64), c["reward"], c["done"], c["w"],
-                                                   packs_done=packs_done, update_tree=side)
+                                                   packs_done=packs_done, update_tree=side, early_update=True)
             else:
                 idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
                 b = st.gather(idx)
@@ -633,7 +671,9 @@ class Learner:
             self.launches_per_step = lib.b2rl_launch_count() - c0
             return r
         self.optim.zero_grad(set_to_none=False)
-        side = torch.cuda.Stream(self.device)
+        # The step's main branch is captured on a HIGH-priority stream (kernel nodes inherit it): the side branches
+        # (weight gradients, early optimizer step, operand packs) only fill SMs the critical chain leaves idle.
+        side = torch.cuda.Stream(self.device, priority=-2)
         # The ingest thread keeps pushing on the same replay handle: hold its lock so that no cudaMalloc /
         # cudaHostAlloc / copy of that thread lands inside the warm-up or the (global-mode) capture.
         with self.memory._lock:
@@ -645,7 +685,7 @@ class Learner:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             c0 = lib.b2rl_launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):
                 self._static = body()
             self.launches_per_step = lib.b2rl_launch_count() - c0   # recorded into the graph, replayed each step
         self._graph = g

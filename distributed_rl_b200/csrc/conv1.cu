@@ -21,15 +21,18 @@
 // instructions per tile instead of 8 and twice the im2col bytes, and measured 1.4-1.6x slower —
 // tcgen05.mma issue costs ~70 cycles per instruction here; profiles/r01_conv1.md.)
 //
-// Warp roles per CTA (persistent, one CTA per SM, 16 warps):
+// Warp roles per CTA (persistent, one CTA per SM, 28 warps):
 //   warp 0       TMA loader: weights once, then one 28 224-byte frame stack per item
 //   warp 1       MMA issuer (one elected thread): 8 x tcgen05.mma (K = 32) per 128-row tile
 //   warp 2       TMEM allocator
 //   warps 4-11   im2col producers: SMEM frame -> 128B-swizzled K-major A tile (uint8);
 //                thread = (tile row, channel pair)
-//   warps 12-19  epilogue, two groups of 4 (one per TMEM lane quarter): group g takes network g
-//                (with one network group 1 idles): tcgen05.ld -> recombine digits -> scale ->
-//                ReLU -> swizzled SMEM block -> coalesced 512-byte global stores
+//   warps 12-27  epilogue, four groups of 4 (one warp per TMEM lane quarter = four epilogue warps per SM
+//                sub-partition; a single warp per sub-partition was dependent-issue-latency bound at ~2.2 k
+//                cycles per tile, profiles/r02_conv1.md).  The accumulator is buffered 4 / n_nets deep in
+//                TMEM and group g takes network g % n_nets of the tiles in buffer g / n_nets:
+//                tcgen05.ld -> recombine digits -> scale -> ReLU -> swizzled SMEM block -> stores of
+//                full 64-byte segments (16 channels at a time, 72 registers per thread)
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -46,11 +49,12 @@ constexpr int TILE_M = 128;
 constexpr int TILES = (POS + TILE_M - 1) / TILE_M; // 4 (the last one has 16 valid rows)
 constexpr int NSPLIT = 4;
 constexpr int A_STAGES = 2;
-constexpr int STAGE_OUT_BYTES = 8 * 32 * 128;      // epilogue staging: 8 warps x 32 rows x 128 B
+constexpr int EPI_WARPS = 16;
+constexpr int STAGE_OUT_BYTES = EPI_WARPS * 32 * 64;   // epilogue staging: 16 warps x 32 rows x 64 B
 constexpr int A_TILE_BYTES = TILE_M * K_TOTAL;     // 32 768: 2 K-chunks x 128 rows x 128 B
 constexpr int A_CHUNK_BYTES = TILE_M * 128;        // 16 384
 constexpr int RAW_STRIDE = 28288;                  // FRAME_BYTES rounded up to 128
-constexpr int THREADS = 640;                       // 20 warps: 3 role warps, 1 spare, 8 producers, 8 epilogue
+constexpr int THREADS = 896;                       // 28 warps: 3 role warps, 1 spare, 8 producers, 16 epilogue
 constexpr int PRODUCERS = 256;
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -98,6 +102,19 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -160,14 +177,22 @@ struct Params {
   long long* dbg;            // optional [gridDim.x][16] cycle counters (B2RL_CONV1_DBG=1), else nullptr
 };
 
-template <int N_NETS, int C_OUT>
+// PROBE = per-role cycle counters (B2RL_CONV1_DBG=1); compiled out of the production instantiation
+template <bool PROBE>
+__device__ __forceinline__ long long pclk() {
+  if constexpr (PROBE) return clock64();
+  else return 0;
+}
+
+template <int N_NETS, int C_OUT, bool PROBE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_conv1_fused(const __grid_constant__ Params P) {
   constexpr int N_PER_NET = NSPLIT * C_OUT;            // MMA columns per network: 128 (64 for 16 channels)
   constexpr int N_TOTAL = N_NETS * N_PER_NET;          // MMA N: 64 .. 256
   constexpr int ROW_BYTES = C_OUT * 4;                 // one output position of one network
   constexpr int B_BYTES = N_TOTAL * K_TOTAL;           // 32 / 64 KiB
-  constexpr uint32_t TMEM_COLS = 2 * N_TOTAL;          // double-buffered accumulator
+  constexpr int NBUF = 4 / N_NETS;                     // accumulator buffers in TMEM: 4 (one network) / 2
+  constexpr uint32_t TMEM_COLS = NBUF * N_TOTAL;       // 4 * N_PER_NET = 512 (32 channels) / 256 columns
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B atoms must be 1024-byte aligned in the shared window: align by hand (1 KiB slack reserved)
   uint8_t* smem = smem_raw + ((1024u - (sptr(smem_raw) & 1023u)) & 1023u);
@@ -176,7 +201,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
   uint8_t* sRaw = sA + A_STAGES * A_TILE_BYTES;
   uint8_t* sOut = sRaw + 2 * RAW_STRIDE;       // per-epilogue-warp 4 KiB transpose buffers
   __shared__ __align__(8) uint64_t b_full, raw_full[2], raw_empty[2], a_full[A_STAGES], a_empty[A_STAGES],
-      t_full[2], t_empty[2];
+      t_full[4], t_empty[4];
   __shared__ uint32_t s_tmem;
   __shared__ float s_scale[2 * C_OUT_MAX];
   if (threadIdx.x < N_NETS * C_OUT) s_scale[threadIdx.x] = P.scale[threadIdx.x] * (1.0f / 128.0f);   // exact
@@ -186,7 +211,7 @@ k_conv1_fused(const __grid_constant__ Params P) {
     mbar_init(&b_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], PRODUCERS); }
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], PRODUCERS); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 256); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], N_NETS * 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -199,7 +224,12 @@ k_conv1_fused(const __grid_constant__ Params P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const int64_t first = blockIdx.x, stride = gridDim.x;
+  // Work is split by (frame stack, 128-row tile) unit, not by frame stack: 512 stacks over 148 CTAs would be
+  // 4 vs 3.46 stacks (16 vs 13.8 tiles); a CTA takes a contiguous run of units and loads every stack it touches.
+  const int64_t units = P.n * TILES;
+  const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+  const int64_t k_first = u0 / TILES, k_end = (u1 + TILES - 1) / TILES;   // stacks [k_first, k_end)
+  const long long k_begin = pclk<PROBE>();
 
   if (warp == 0) {
     // ------------------------------ TMA loader ------------------------------
@@ -208,16 +238,18 @@ k_conv1_fused(const __grid_constant__ Params P) {
       constexpr int LOAD_CHUNK = (B_BYTES < 32768) ? B_BYTES : 32768;
       for (int off = 0; off < B_BYTES; off += LOAD_CHUNK) bulk_g2s(sB + off, P.bq + off, LOAD_CHUNK, &b_full);
       int it = 0;
-      for (int64_t k = first; k < P.n; k += stride, ++it) {
+      long long d0 = 0;
+      for (int64_t k = k_first; k < k_end; ++k, ++it) {
         const int s = it & 1;
-        const long long c0 = clock64();
+        const long long c0 = pclk<PROBE>();
         mbar_wait(&raw_empty[s], ((it >> 1) & 1) ^ 1);
-        if (P.dbg) P.dbg[blockIdx.x * 16 + 0] += clock64() - c0;
+        d0 += pclk<PROBE>() - c0;
         int64_t row = P.idx ? P.idx[k] : k;
         row = row < 0 ? 0 : (row >= P.capacity ? P.capacity - 1 : row);
         mbar_expect_tx(&raw_full[s], FRAME_BYTES);
         bulk_g2s(sRaw + s * RAW_STRIDE, P.frames + row * FRAME_BYTES, FRAME_BYTES, &raw_full[s]);
       }
+      if (PROBE) P.dbg[blockIdx.x * 16 + 0] = d0;
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
@@ -226,14 +258,16 @@ k_conv1_fused(const __grid_constant__ Params P) {
       mbar_wait(&b_full, 0);
       tc_fence_after();
       int at = 0;   // A-tile counter
-      for (int64_t k = first; k < P.n; k += stride) {
-        for (int t = 0; t < TILES; ++t, ++at) {
-          const int stage = at % A_STAGES, acc = at & 1;
-          const long long c0 = clock64();
-          mbar_wait(&t_empty[acc], ((at >> 1) & 1) ^ 1);
-          const long long c1 = clock64();
+      long long d1 = 0, d2 = 0, d3 = 0;
+      for (int64_t k = k_first; k < k_end; ++k) {
+        const int t_lo = (int)max((int64_t)0, u0 - k * TILES), t_hi = (int)min((int64_t)TILES, u1 - k * TILES);
+        for (int t = t_lo; t < t_hi; ++t, ++at) {
+          const int stage = at % A_STAGES, acc = at % NBUF;
+          const long long c0 = pclk<PROBE>();
+          mbar_wait(&t_empty[acc], ((at / NBUF) & 1) ^ 1);
+          const long long c1 = pclk<PROBE>();
           mbar_wait(&a_full[stage], (at / A_STAGES) & 1);
-          const long long c2 = clock64();
+          const long long c2 = pclk<PROBE>();
           tc_fence_after();
           const uint32_t a_base = sptr(sA + stage * A_TILE_BYTES), b_base = sptr(sB);
           const uint32_t d = tmem + (uint32_t)(acc * N_TOTAL);
@@ -245,12 +279,15 @@ k_conv1_fused(const __grid_constant__ Params P) {
           }
           tc_commit(&a_empty[stage]);   // SMEM stage reusable once these MMAs have read it
           tc_commit(&t_full[acc]);      // accumulator complete
-          if (P.dbg) {
-            P.dbg[blockIdx.x * 16 + 1] += c1 - c0;
-            P.dbg[blockIdx.x * 16 + 2] += c2 - c1;
-            P.dbg[blockIdx.x * 16 + 3] += clock64() - c2;
-          }
+          d1 += c1 - c0;
+          d2 += c2 - c1;
+          d3 += pclk<PROBE>() - c2;
         }
+      }
+      if (PROBE) {
+        P.dbg[blockIdx.x * 16 + 1] = d1;
+        P.dbg[blockIdx.x * 16 + 2] = d2;
+        P.dbg[blockIdx.x * 16 + 3] = d3;
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -258,19 +295,21 @@ k_conv1_fused(const __grid_constant__ Params P) {
     const int pt = threadIdx.x - 128;            // 0..255
     const int r_local = pt & (TILE_M - 1);       // A-tile row
     const int chalf = pt >> 7;                   // this thread converts channels 2*chalf, 2*chalf+1 (one K chunk)
-    const bool probe = P.dbg && pt == 0;
+    const bool probe = PROBE && pt == 0;
     int at = 0, it = 0;
-    for (int64_t k = first; k < P.n; k += stride, ++it) {
+    long long d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+    for (int64_t k = k_first; k < k_end; ++k, ++it) {
       const int s = it & 1;
-      long long c0 = clock64();
+      long long c0 = pclk<PROBE>();
       mbar_wait(&raw_full[s], (it >> 1) & 1);
-      if (probe) P.dbg[blockIdx.x * 16 + 4] += clock64() - c0;
+      d4 += pclk<PROBE>() - c0;
       const uint8_t* raw = sRaw + s * RAW_STRIDE;
-      for (int t = 0; t < TILES; ++t, ++at) {
+      const int t_lo = (int)max((int64_t)0, u0 - k * TILES), t_hi = (int)min((int64_t)TILES, u1 - k * TILES);
+      for (int t = t_lo; t < t_hi; ++t, ++at) {
         const int stage = at % A_STAGES;
-        c0 = clock64();
+        c0 = pclk<PROBE>();
         mbar_wait(&a_empty[stage], ((at / A_STAGES) & 1) ^ 1);
-        const long long c1 = clock64();
+        const long long c1 = pclk<PROBE>();
         const int p = t * TILE_M + r_local;
         if (p < POS) {
           const int oy = p / OHW, ox = p - oy * OHW;
@@ -291,54 +330,69 @@ k_conv1_fused(const __grid_constant__ Params P) {
             }
           }
         }
-        const long long c2 = clock64();
+        const long long c2 = pclk<PROBE>();
         fence_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&a_full[stage]);
-        if (probe) {
-          P.dbg[blockIdx.x * 16 + 5] += c1 - c0;
-          P.dbg[blockIdx.x * 16 + 6] += c2 - c1;
-          P.dbg[blockIdx.x * 16 + 7] += clock64() - c2;
-        }
+        d5 += c1 - c0;
+        d6 += c2 - c1;
+        d7 += pclk<PROBE>() - c2;
       }
       mbar_arrive(&raw_empty[s]);      // this thread is done reading the raw frame
     }
+    if (probe) {
+      P.dbg[blockIdx.x * 16 + 4] = d4;
+      P.dbg[blockIdx.x * 16 + 5] = d5;
+      P.dbg[blockIdx.x * 16 + 6] = d6;
+      P.dbg[blockIdx.x * 16 + 7] = d7;
+    }
   } else if (warp >= 12) {
     // ------------------------------- epilogue -------------------------------
+    // 16 warps = 4 groups of 4 (one warp per TMEM lane quarter, i.e. four epilogue warps per SM sub-partition,
+    // so one warp's dependent-issue latency is covered by the other three).  Group g takes network g % N_NETS
+    // of every tile whose accumulator buffer is g / N_NETS: with one network the four groups rotate over four
+    // buffers, with two networks two buffers x two networks.
     const int wq = warp & 3;                     // TMEM lane quarter this warp may access
-    const int eg = (warp - 12) >> 2;             // epilogue group 0 / 1
+    const int eg = (warp - 12) >> 2;             // epilogue group 0..3
+    const int net = eg % N_NETS, slot = eg / N_NETS;
     const int r_local = wq * 32 + lane;
-    const bool probe_e = P.dbg && r_local == 0 && eg == 0;
-    int at = 0;
-    for (int64_t k = first; k < P.n; k += stride) {
-      for (int t = 0; t < TILES; ++t, ++at) {
-        const int acc = at & 1;
-        const long long c0 = clock64();
-        mbar_wait(&t_full[acc], (at >> 1) & 1);
-        const long long c1 = clock64();
+    const bool probe_e = PROBE && r_local == 0 && eg == 0;
+    uint8_t* stg = sOut + ((warp - 12) * 2048); // this warp's 32 rows x 64 B (16 channels), 16-byte units XOR-swizzled
+    const float relu_floor = P.relu ? 0.0f : -INFINITY;
+    // staging offsets: a thread writes its own row (lane) and later reads row i*8 + lane/4, unit lane%4
+    const uint32_t st_row = sptr(stg) + lane * 64, st_sw = (lane >> 1) & 3;
+    const uint32_t ld_off = sptr(stg) + (lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4);
+    const int g_off = (lane >> 2) * ROW_BYTES + (lane & 3) * 16;      // byte offset of that unit inside the warp's block
+    int at = 0, own = 0;
+    long long d8 = 0, d9 = 0, d11 = 0, d12 = 0;
+    for (int64_t k = k_first; k < k_end; ++k) {
+      const int t_lo = (int)max((int64_t)0, u0 - k * TILES), t_hi = (int)min((int64_t)TILES, u1 - k * TILES);
+      for (int t = t_lo; t < t_hi; ++t, ++at) {
+        if (at % NBUF != slot) continue;
+        const long long c0 = pclk<PROBE>();
+        mbar_wait(&t_full[slot], own & 1);
+        ++own;
+        const long long c1 = pclk<PROBE>();
         tc_fence_after();
-        const int p = t * TILE_M + r_local;
-        const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N_TOTAL);
-        uint8_t* stg = sOut + (eg * 4 + wq) * 4096; // this warp's 32 rows x 128 B, 16-byte units XOR-swizzled
-        const float relu_floor = P.relu ? 0.0f : -INFINITY;
+        const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * N_TOTAL + net * N_PER_NET);
         const int rows_valid = POS - (t * TILE_M + wq * 32);   // rows of this warp's block that exist (<= 0: none)
-        {
-          const int net = (N_NETS == 2) ? eg : 0;
-          const bool active = (N_NETS == 2) || eg == 0;   // one network: group 0 does it all (full-line stores)
+        uint8_t* obase = reinterpret_cast<uint8_t*>(
+            P.out + (((int64_t)net * P.n + k) * POS + (t * TILE_M + wq * 32)) * C_OUT);
 #pragma unroll
-          for (int h = 0; h < C_OUT / 16; ++h) {
-            if (!active) break;
-            int32_t q0[16], q1[16], q2[16], q3[16];
-            const uint32_t col = tbase + net * N_PER_NET + h * 16;
-            const long long e0 = clock64();
-            tc_ld16(col + 0 * C_OUT, q0);
-            tc_ld16(col + 1 * C_OUT, q1);
-            tc_ld16(col + 2 * C_OUT, q2);
-            tc_ld16(col + 3 * C_OUT, q3);
+        for (int h = 0; h < C_OUT / 16; ++h) {
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            int32_t q0[8], q1[8], q2[8], q3[8];
+            const uint32_t col = tbase + h * 16 + c8 * 8;
+            const long long e0 = pclk<PROBE>();
+            tc_ld8(col + 0 * C_OUT, q0);
+            tc_ld8(col + 1 * C_OUT, q1);
+            tc_ld8(col + 2 * C_OUT, q2);
+            tc_ld8(col + 3 * C_OUT, q3);
             tc_wait_ld();
-            if (probe_e) P.dbg[blockIdx.x * 16 + 11] += clock64() - e0;
-            const float* sc = s_scale + net * C_OUT + h * 16;
+            d11 += pclk<PROBE>() - e0;
+            const float* sc = s_scale + net * C_OUT + h * 16 + c8 * 8;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
               float y[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -351,38 +405,47 @@ k_conv1_fused(const __grid_constant__ Params P) {
                 const float v = __fmaf_rn(ft, 1.0f / 16384.0f, fu) * sc[i];   // sc already holds s_c / (255 * 2^7)
                 y[e] = fmaxf(v, relu_floor);
               }
-              const int unit = h * 4 + g;            // 16-byte unit of this row's 128 B
-              *reinterpret_cast<float4*>(stg + lane * 128 + ((unit ^ (lane & 7)) << 4)) =
-                  make_float4(y[0], y[1], y[2], y[3]);
+              const uint32_t unit = c8 * 2 + g;      // 16-byte unit of this row's 64-byte half
+              st_shared_v4(st_row + ((unit ^ st_sw) << 4), y[0], y[1], y[2], y[3]);
             }
           }
           __syncwarp();
-          // the warp's 32 rows are contiguous in the NHWC output (4 KiB at 32 channels): coalesced 512-byte stores
-          if (rows_valid > 0) {
-            float* obase = P.out + (((int64_t)net * P.n + k) * POS + (t * TILE_M + wq * 32)) * C_OUT;
+          // 32 rows x 64 B of this half: every store instruction writes eight full 64-byte segments
+          // (the whole block is contiguous when C_OUT = 16)
+          if (rows_valid >= 32) {
 #pragma unroll
-            for (int i = 0; i < ROW_BYTES / 16; ++i) {
-              const int off = (i * 32 + lane) * 16;          // byte offset inside the warp's contiguous block
-              const int row = off / ROW_BYTES, unit = (off % ROW_BYTES) >> 4;
-              if (row < rows_valid && active) {
-                const float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
-                *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(obase) + off) = v;
+            for (int i = 0; i < 4; ++i) {
+              const float4 v = ld_shared_v4(ld_off + i * 512);
+              *reinterpret_cast<float4*>(obase + g_off + h * 64 + i * 8 * ROW_BYTES) = v;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i * 8 + (lane >> 2) < rows_valid) {
+                const float4 v = ld_shared_v4(ld_off + i * 512);
+                *reinterpret_cast<float4*>(obase + g_off + h * 64 + i * 8 * ROW_BYTES) = v;
               }
             }
           }
           __syncwarp();
         }
         tc_fence_before();
-        mbar_arrive(&t_empty[acc]);
-        if (probe_e) {
-          P.dbg[blockIdx.x * 16 + 8] += c1 - c0;
-          P.dbg[blockIdx.x * 16 + 9] += clock64() - c1;
-        }
+        mbar_arrive(&t_empty[slot]);
+        d8 += c1 - c0;
+        d9 += pclk<PROBE>() - c1;
+        if (own == 1) d12 = c1 - k_begin;
       }
+    }
+    if (probe_e) {
+      P.dbg[blockIdx.x * 16 + 8] = d8;
+      P.dbg[blockIdx.x * 16 + 9] = d9;
+      P.dbg[blockIdx.x * 16 + 11] = d11;
+      P.dbg[blockIdx.x * 16 + 12] = d12;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PROBE && threadIdx.x == 0) P.dbg[blockIdx.x * 16 + 10] = pclk<PROBE>() - k_begin;
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
   }
@@ -411,20 +474,25 @@ extern "C" int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, 
   return B2RL_OK;
 }
 
-template <int N_NETS, int C_OUT>
-static cudaError_t conv1_launch(const conv1::Params& P, unsigned grid, cudaStream_t st) {
+template <int N_NETS, int C_OUT, bool PROBE>
+static cudaError_t conv1_launch_p(const conv1::Params& P, unsigned grid, cudaStream_t st) {
   static bool attr[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!attr[dev & 63]) {
-    e = cudaFuncSetAttribute(conv1::k_conv1_fused<N_NETS, C_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(conv1::k_conv1_fused<N_NETS, C_OUT, PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)conv1::smem_bytes<N_NETS, C_OUT>());
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  conv1::k_conv1_fused<N_NETS, C_OUT><<<grid, conv1::THREADS, conv1::smem_bytes<N_NETS, C_OUT>(), st>>>(P);
+  conv1::k_conv1_fused<N_NETS, C_OUT, PROBE><<<grid, conv1::THREADS, conv1::smem_bytes<N_NETS, C_OUT>(), st>>>(P);
   return cudaSuccess;
+}
+
+template <int N_NETS, int C_OUT>
+static cudaError_t conv1_launch(const conv1::Params& P, unsigned grid, cudaStream_t st) {
+  return P.dbg ? conv1_launch_p<N_NETS, C_OUT, true>(P, grid, st) : conv1_launch_p<N_NETS, C_OUT, false>(P, grid, st);
 }
 
 extern "C" int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
@@ -446,7 +514,8 @@ extern "C" int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, con
   if (getenv("B2RL_CONV1_DBG") && !dbg_buf) B2RL_CUDA(cudaMalloc(&dbg_buf, 256 * 16 * sizeof(long long)));
   if (dbg_buf) B2RL_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * 16 * sizeof(long long), (cudaStream_t)stream));
   conv1::Params P{frames_dev, idx_dev, n, capacity, bq_dev, scale_dev, out_dev, relu, dbg_buf};
-  const unsigned grid = (unsigned)((n < sms[dev & 63]) ? n : sms[dev & 63]);
+  const int64_t units = n * conv1::TILES;
+  const unsigned grid = (unsigned)((units < sms[dev & 63]) ? units : sms[dev & 63]);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (c_out == 32) e = (n_nets == 1) ? conv1_launch<1, 32>(P, grid, st) : conv1_launch<2, 32>(P, grid, st);
@@ -457,10 +526,11 @@ extern "C" int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, con
   if (dbg_buf) {   // profiling aid: per-role cycle counters of CTA 0 (synchronous; never set in production)
     long long h[16];
     B2RL_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-    static const char* names[12] = {"loader:wait raw_empty", "mma:wait t_empty", "mma:wait a_full", "mma:issue+commit",
+    static const char* names[13] = {"loader:wait raw_empty", "mma:wait t_empty", "mma:wait a_full", "mma:issue+commit",
                                     "prod:wait raw_full", "prod:wait a_empty", "prod:build", "prod:fence+arrive",
-                                    "epi:wait t_full", "epi:work", "(unused)", "epi:tcgen05.ld+wait"};
-    for (int i = 0; i < 12; ++i)
+                                    "epi:wait t_full", "epi:work", "roles total (CTA 0)", "epi:tcgen05.ld+wait",
+                                    "first accumulator ready at"};
+    for (int i = 0; i < 13; ++i)
       fprintf(stderr, "[conv1 dbg] n_nets %d n %lld %-24s %lld\n", n_nets, (long long)n, names[i], h[i]);
   }
   return B2RL_OK;

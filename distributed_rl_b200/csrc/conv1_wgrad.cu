@@ -398,22 +398,31 @@ k_conv1_wgrad(const __grid_constant__ Params P) {
   }
 }
 
-// dW[i] (+)= sum over CTAs of partial[cta][i], accumulated in fp64 in CTA order (deterministic)
-__global__ void __launch_bounds__(256)
+// dW[i] (+)= sum over CTAs of partial[cta][i] in fp64, fixed order (deterministic, no atomics).
+// Block = 32 outputs x 8 slices of the partials: slice j adds partials j, j+8, ... (about 19 independent coalesced
+// loads per thread instead of a 148-long chain: the kernel is L2-latency bound), then the 8 slices are added in order.
+constexpr int RED_SLICES = 8;
+__global__ void __launch_bounds__(32 * RED_SLICES)
 k_conv1_wgrad_reduce(const float* __restrict__ partial, int n_parts, int numel, int accumulate, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= numel) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four interleaved chains (fixed order): four loads in flight
-  int p = 0;
-  for (; p + 3 < n_parts; p += 4) {
-    s0 += (double)partial[(int64_t)p * numel + i];
-    s1 += (double)partial[(int64_t)(p + 1) * numel + i];
-    s2 += (double)partial[(int64_t)(p + 2) * numel + i];
-    s3 += (double)partial[(int64_t)(p + 3) * numel + i];
+  __shared__ double s_part[RED_SLICES][32];
+  const int i = blockIdx.x * 32 + threadIdx.x, j = threadIdx.y;
+  double s0 = 0.0, s1 = 0.0;
+  if (i < numel) {
+    int p = j;
+    for (; p + RED_SLICES < n_parts; p += 2 * RED_SLICES) {
+      s0 += (double)partial[(int64_t)p * numel + i];
+      s1 += (double)partial[(int64_t)(p + RED_SLICES) * numel + i];
+    }
+    if (p < n_parts) s0 += (double)partial[(int64_t)p * numel + i];
   }
-  for (; p < n_parts; ++p) s0 += (double)partial[(int64_t)p * numel + i];
-  const double s = (s0 + s1) + (s2 + s3);
-  out[i] = accumulate ? (float)((double)out[i] + s) : (float)s;
+  s_part[j][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (j == 0 && i < numel) {
+    double s = s_part[0][threadIdx.x];
+#pragma unroll
+    for (int q = 1; q < RED_SLICES; ++q) s += s_part[q][threadIdx.x];
+    out[i] = accumulate ? (float)((double)out[i] + s) : (float)s;
+  }
 }
 
 template <int C_OUT>
@@ -478,8 +487,8 @@ extern "C" int b2rl_conv1_wgrad(const uint8_t* frames_dev, int64_t capacity, con
     B2RL_CUDA(c_out == 32 ? wgrad_launch<32>(P, grid, st) : wgrad_launch<16>(P, grid, st));
     count_launch();
     B2RL_CHECK_LAUNCH();
-    conv1w::k_conv1_wgrad_reduce<<<(numel + 63) / 64, 64, 0, st>>>(workspace_dev, (int)grid, numel,
-                                                                       (accumulate || off > 0) ? 1 : 0, gw_dev);
+    conv1w::k_conv1_wgrad_reduce<<<(numel + 31) / 32, dim3(32, conv1w::RED_SLICES), 0, st>>>(
+        workspace_dev, (int)grid, numel, (accumulate || off > 0) ? 1 : 0, gw_dev);
     count_launch();
     B2RL_CHECK_LAUNCH();
   }

@@ -116,3 +116,13 @@ extern "C" int b2rl_rmsprop_step(float* const* params, float* const* grads, floa
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;
 }
+
+extern "C" int b2rl_rmsprop_norm_finish(double* sumsq_scratch_dev, int32_t n_tensors, float* grad_norm_out_dev,
+                                        void* stream) {
+  B2RL_REQUIRE(sumsq_scratch_dev && grad_norm_out_dev, "null argument");
+  B2RL_REQUIRE(n_tensors >= 1 && n_tensors <= OPT_MAX_TENSORS, "1..24 tensors");
+  k_grad_norm_finish<<<1, 32, 0, (cudaStream_t)stream>>>(sumsq_scratch_dev, n_tensors, grad_norm_out_dev);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}

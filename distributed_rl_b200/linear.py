@@ -29,37 +29,57 @@ class WeightGradSink:
 
     def __init__(self, device):
         self.device = torch.device(device)
-        self.stream = torch.cuda.Stream(self.device)
-        self._fork, self._done = torch.cuda.Event(), torch.cuda.Event()
-        self._keep, self._pending = [], False
+        # two lanes: the heads' weight gradients (the big GEMM + its operand packs) and the convolution stack's.
+        # On one stream the conv_2 / conv_3 weight gradients queued behind the heads' and ran alone at the very end
+        # of backward (profiles/r02_timeline.txt); on their own lane they overlap the dgrad chain.
+        # Priorities (captured into the step's graph nodes): the learner's main branch runs at -2, the convolution
+        # lane at -1 (its kernels must finish before the SM-filling conv_1 weight-gradient kernel starts), the
+        # heads' lane (6.4 MB GEMM operands, the early optimizer step) at 0 fills what is left.
+        self.stream = torch.cuda.Stream(self.device, priority=0)
+        self.streams = (self.stream, torch.cuda.Stream(self.device, priority=-1))
+        self._fork = (torch.cuda.Event(), torch.cuda.Event())
+        self._done = (torch.cuda.Event(), torch.cuda.Event())
+        self._keep, self._pending = [], [False, False]
+        self._lane, self.accumulated = 0, (set(), set())   # per lane: ids of the params accumulated since the last join
         self.on_ready = {}          # id(param) -> callable, invoked (side stream) after that param's grad is complete
 
     @staticmethod
     def usable(params) -> bool:
         return _SINK is not None and all(p.grad is not None for p in params)
 
-    def submit(self, fn, keep=()):
+    def submit(self, fn, keep=(), lane: int = 0):
         cur = torch.cuda.current_stream(self.device)
-        self._fork.record(cur)
-        self.stream.wait_event(self._fork)
-        with torch.cuda.stream(self.stream):
+        self._fork[lane].record(cur)
+        self.streams[lane].wait_event(self._fork[lane])
+        self._lane = lane
+        with torch.cuda.stream(self.streams[lane]):
             fn()
         self._keep.extend(keep)
-        self._pending = True
+        self._pending[lane] = True
+
+    def run_on_lane(self, fn, lane: int = 0):
+        """Queue fn behind what the lane already holds, without a new dependency on the caller's stream."""
+        with torch.cuda.stream(self.streams[lane]):
+            fn()
+        self._pending[lane] = True
 
     def accumulate(self, param, grad):
         """(side stream) param.grad += grad, then the parameter's ready callback."""
         param.grad.add_(grad)
+        self.accumulated[self._lane].add(id(param))
         cb = self.on_ready.get(id(param))
         if cb is not None:
             cb(param)
 
     def join(self):
-        if self._pending:
-            self._done.record(self.stream)
-            torch.cuda.current_stream(self.device).wait_event(self._done)
-            self._pending = False
+        for lane in (0, 1):
+            if self._pending[lane]:
+                self._done[lane].record(self.streams[lane])
+                torch.cuda.current_stream(self.device).wait_event(self._done[lane])
+                self._pending[lane] = False
         self._keep.clear()
+        self.accumulated[0].clear()
+        self.accumulated[1].clear()
 
     def active(self):
         return _SinkContext(self)
@@ -235,12 +255,9 @@ class _Linear3x(torch.autograd.Function):
         N = sum(w.shape[0] for w in ws)
         gy = gy.contiguous()
         gx, gws = None, [None] * len(ws)
-        if ctx.needs_input_grad[0]:
-            # dx[M][K] = gy[M][N] @ W[N][K]: contraction over N, the B operand is W^T ([K rows][N])
-            bt = ctx.cache.get("bwdT") if ctx.cache is not None else None     # prepared ahead (GraphAgent.prepack_heads)
-            gx = gemm_packed(split_pack(gy, False, False), bt if bt is not None else _pack_pieces(ws, True, True), M, K, N)
         if any(ctx.needs_input_grad[2:]):
-            # dW[N][K] = gy^T[N][M] @ x[M][K]: contraction over M
+            # dW[N][K] = gy^T[N][M] @ x[M][K]: contraction over M.  Submitted before dx is launched, so the sink's
+            # lane forks from the stream as it is now and runs beside the dx GEMM, not behind it.
             def wgrad():
                 gw = gemm_packed(split_pack(gy, True, False), split_pack(x, True, True), N, K, M)
                 return list(torch.split(gw, [w.shape[0] for w in ws], 0))
@@ -253,6 +270,10 @@ class _Linear3x(torch.autograd.Function):
                 sink.submit(deferred, keep=(gy, x))
             else:
                 gws = wgrad()
+        if ctx.needs_input_grad[0]:
+            # dx[M][K] = gy[M][N] @ W[N][K]: contraction over N, the B operand is W^T ([K rows][N])
+            bt = ctx.cache.get("bwdT") if ctx.cache is not None else None     # prepared ahead (GraphAgent.prepack_heads)
+            gx = gemm_packed(split_pack(gy, False, False), bt if bt is not None else _pack_pieces(ws, True, True), M, K, N)
         return (gx, None, *gws)
 
 
@@ -285,17 +306,11 @@ class _ReluFlatLinear3x(torch.autograd.Function):
         N, K = sum(w.shape[0] for w in ws), C * H * W
         gh = gh.contiguous()
         gy, gws = None, [None] * len(ws)
-        if ctx.needs_input_grad[0]:
-            bt = ctx.cache.get("bwdT") if ctx.cache is not None else None
-            gx = gemm_packed(split_pack(gh, False, False), bt if bt is not None else _pack_pieces(ws, True, True), B, K, N)
-            gy = torch.empty_like(y)                                         # channels_last like y
-            _lib.check(_lib.load().b2rl_unflatten_relu_mask(gx.data_ptr(), gx.stride(0), y.data_ptr(), B, H * W, C,
-                                                           gy.data_ptr(), _stream()))
         if any(ctx.needs_input_grad[2:]):
             def wgrad():
                 gw = gemm_packed(split_pack(gh, True, False), pack_act_nhwc(y, True), N, K, B)
                 return list(torch.split(gw, [w.shape[0] for w in ws], 0))
-            if WeightGradSink.usable(ws):
+            if WeightGradSink.usable(ws):       # before dL/dy is launched: runs beside it (see _Linear3x.backward)
                 sink = _SINK
 
                 def deferred():
@@ -304,6 +319,12 @@ class _ReluFlatLinear3x(torch.autograd.Function):
                 sink.submit(deferred, keep=(gh, y))
             else:
                 gws = wgrad()
+        if ctx.needs_input_grad[0]:
+            bt = ctx.cache.get("bwdT") if ctx.cache is not None else None
+            gx = gemm_packed(split_pack(gh, False, False), bt if bt is not None else _pack_pieces(ws, True, True), B, K, N)
+            gy = torch.empty_like(y)                                         # channels_last like y
+            _lib.check(_lib.load().b2rl_unflatten_relu_mask(gx.data_ptr(), gx.stride(0), y.data_ptr(), B, H * W, C,
+                                                           gy.data_ptr(), _stream()))
         return (gy, None, *gws)
 
 

@@ -41,15 +41,49 @@ class FusedRMSprop:
         self._numel = (C.c_int64 * n)(*[p.numel() for p in self.params])
         self._arr = arr
 
-    def step(self, want_norm: bool = True) -> torch.Tensor:
-        """Update + zero_grad.  Returns the device scalar sqrt(sum_i ||g_i||_2) (of the pre-step grads)."""
-        g = self._arr(*[p.grad.data_ptr() for p in self.params])
-        for p in self.params:
+    def _launch(self, lo: int, hi: int, norm_out) -> None:
+        """Update + zero_grad of tensors [lo, hi); their squared gradient norms land in scratch slots [lo, hi)."""
+        n = hi - lo
+        sub = lambda a: (C.c_void_p * n)(*a[lo:hi])       # noqa: E731
+        for p in self.params[lo:hi]:
             assert p.grad.stride() == p.stride()
         check(_lib.load().b2rl_rmsprop_step(
-            self._p, g, self._sq, self._ga, self._numel, len(self.params), self.lr, self.alpha, self.eps,
-            int(self.centered), self._scratch.data_ptr(), self.grad_norm.data_ptr() if want_norm else None,
+            sub(self._p), (C.c_void_p * n)(*[p.grad.data_ptr() for p in self.params[lo:hi]]), sub(self._sq),
+            sub(self._ga) if self.centered else None, (C.c_int64 * n)(*self._numel[lo:hi]), n, self.lr, self.alpha,
+            self.eps, int(self.centered), self._scratch.data_ptr() + 8 * lo, norm_out,
             torch.cuda.current_stream(self.device).cuda_stream))
+
+    def set_early(self, params) -> bool:
+        """Name the parameters whose gradients are final before the end of backward (the dense heads): step_early()
+        updates them on whatever stream is current while the rest of backward runs, step() then only does the others.
+        Valid because the update has no cross-parameter term (no clipping: APE_X/Learner.py:123-138).  The early
+        parameters must be a contiguous run of the optimizer's list; returns False (and changes nothing) otherwise."""
+        idx = sorted(i for i, p in enumerate(self.params) if any(p is q for q in params))
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            return False
+        self._early = (idx[0], idx[-1] + 1)
+        return True
+
+    def step_early(self) -> None:
+        lo, hi = self._early
+        self._launch(lo, hi, None)
+        self._early_done = True
+
+    def step(self, want_norm: bool = True) -> torch.Tensor:
+        """Update + zero_grad.  Returns the device scalar sqrt(sum_i ||g_i||_2) (of the pre-step grads)."""
+        n = len(self.params)
+        if getattr(self, "_early_done", False):
+            lo, hi = self._early
+            self._early_done = False
+            if lo > 0:
+                self._launch(0, lo, None)
+            if hi < n:
+                self._launch(hi, n, None)
+            if want_norm:
+                check(_lib.load().b2rl_rmsprop_norm_finish(self._scratch.data_ptr(), n, self.grad_norm.data_ptr(),
+                                                           torch.cuda.current_stream(self.device).cuda_stream))
+            return self.grad_norm
+        self._launch(0, n, self.grad_norm.data_ptr() if want_norm else None)
         return self.grad_norm
 
     def zero_grad(self, set_to_none: bool = False) -> None:

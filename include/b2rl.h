@@ -267,6 +267,12 @@ int b2rl_rmsprop_step(float* const* params, float* const* grads, float* const* s
                       float* const* grad_avg, const int64_t* numel, int32_t n_tensors, double lr, double alpha,
                       double eps, int32_t centered, double* sumsq_scratch_dev, float* grad_norm_out_dev,
                       void* stream);
+/* The same update issued in two parts: Learner.step (APE_X/Learner.py:123-138) has no gradient clipping, so a
+ * parameter can be updated as soon as its own gradient is final — the dense heads' (97 % of the elements) while the
+ * convolution stack's backward still runs.  Each part calls b2rl_rmsprop_step on its tensors with
+ * grad_norm_out_dev = NULL and sumsq_scratch_dev pointing at its slots of one n-entry scratch; this call then forms
+ * the reference's "norm" sqrt(sum_i ||g_i||_2) (:130) over all n slots and re-zeroes them. */
+int b2rl_rmsprop_norm_finish(double* sumsq_scratch_dev, int32_t n_tensors, float* grad_norm_out_dev, void* stream);
 
 /* The dense heads of the networks (nn.Linear, bias-free: baseline/baseNetwork.py:77-79; 3136 -> 512
  * adv/val heads cfg/ape_x.json:52-71) at fp32 accuracy on the tensor cores: every fp32 operand is

@@ -25,7 +25,7 @@ def _mk(apex, B=32, N=4096, seed=0, **kw):
     L = apex.Learner(cfg, connect=None, start_replay=False)
     with torch.no_grad():
         for p in L.target_model.parameters():
-            p.add_(0.01 * torch.randn_like(p))
+            p.add_(0.01 * torch.randn(p.shape, device=p.device))    # by logical index: independent of the memory format
     return cfg, L
 
 
@@ -141,7 +141,7 @@ def test_r2d2_learner_train_matches_oracle_and_autograd():
     L = r2d2.Learner(cfg)
     with torch.no_grad():
         for p in L.target_model.parameters():
-            p.add_(0.02 * torch.randn_like(p))
+            p.add_(0.02 * torch.randn(p.shape, device=p.device))
     ref_model = copy.deepcopy(L.model)
     ref_opt = r2d2.make_optimizer(cfg.OPTIM_INFO, ref_model.getParameters(), capturable=False)
     rng = np.random.default_rng(0)
@@ -323,6 +323,40 @@ def test_fused_rmsprop_matches_torch_optim(centered, eps, alpha):
         for p, q in zip(ref, mine):
             np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-6, atol=2e-8)
             assert float(q.grad.abs().max()) == 0.0            # zero_grad fused
+
+
+def test_fused_rmsprop_early_late_split_equals_one_step():
+    """The optimizer step issued in two parts (dense heads early, the rest + the 'norm' later: optim.set_early /
+    step_early / step, b2rl_rmsprop_norm_finish) is bit-identical to the single launch — parameters, optimizer state,
+    zeroed gradients — and gives the same 'norm' (APE_X/Learner.py:123-138 has no cross-parameter term)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributed_rl_b200.optim import FusedRMSprop
+    torch.manual_seed(1)
+    shapes = [(32, 4, 8, 8), (64, 32, 4, 4), (512, 3136), (6, 512), (512, 3136), (1, 512)]
+    a = [(torch.randn(s, device="cuda") * 0.1).requires_grad_(True) for s in shapes]
+    b = [p.detach().clone().requires_grad_(True) for p in a]
+    one = FusedRMSprop(a, lr=6.25e-5, alpha=0.95, eps=1.5e-7, centered=True)
+    two = FusedRMSprop(b, lr=6.25e-5, alpha=0.95, eps=1.5e-7, centered=True)
+    assert not two.set_early([b[0], b[2]])            # not a contiguous run: refused, nothing changes
+    assert two.set_early(b[2:])
+    side = torch.cuda.Stream()
+    for step in range(3):
+        gs = [torch.randn(s, device="cuda") * (0.5 + step) for s in shapes]
+        for p, q, g in zip(a, b, gs):
+            p.grad.copy_(g)
+            q.grad.copy_(g)
+        n1 = one.step().clone()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            two.step_early()
+        torch.cuda.current_stream().wait_stream(side)
+        n2 = two.step().clone()
+        np.testing.assert_allclose(float(n2), float(n1), rtol=1e-6)      # fp64 atomics: order-dependent at 1e-16
+        assert float(n1) > 0
+        for p, q, s1, s2, g1, g2 in zip(a, b, one.square_avg, two.square_avg, one.grad_avg, two.grad_avg):
+            assert torch.equal(p, q) and torch.equal(s1, s2) and torch.equal(g1, g2)
+            assert float(q.grad.abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("fused", [False, True])

@@ -36,7 +36,7 @@ def test_r2d2_fused_step_equals_train_on_the_staged_batch(pool):
         L = r2d2.Learner(cfg)
         with torch.no_grad():
             for p in L.target_model.parameters():
-                p.add_(0.02 * torch.randn_like(p))
+                p.add_(0.02 * torch.randn(p.shape, device=p.device))
         init = [p.detach().clone() for p in L.model.parameters()]
         rng = np.random.default_rng(5)
         n = pool or N
