@@ -53,6 +53,8 @@ SIGNATURES = {
     "b2rl_rmsprop_step": (C.c_int, [C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                     C.POINTER(c_i64), c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp]),
     "b2rl_rmsprop_norm_finish": (C.c_int, [c_vp, c_i32, c_vp, c_vp]),
+    "b2rl_peer_allreduce_max_ctas": (c_i32, []),
+    "b2rl_peer_allreduce_mean": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "b2rl_gemm_packed_floats": (c_i64, [c_i64, c_i64, c_i32]),
     "b2rl_gemm_split_pack": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "b2rl_gemm_split_pack_into": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),

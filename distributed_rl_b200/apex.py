@@ -353,7 +353,14 @@ class Learner:
         # backward pass: their all-reduce overlaps the backward of the convolution stack
         import os
         heads = [p for p in self.model.getParameters() if p.dim() == 2]
-        self._bucket.enable_overlap([] if os.environ.get("B2RL_NO_OVERLAP") else heads)
+        if os.environ.get("B2RL_NO_OVERLAP"):
+            heads = []
+        self._bucket.enable_overlap(heads)
+        # What is left after backward (the convolution stack's 0.3 MB) is the collective on the critical path: one
+        # libb2rl kernel over NVLink peer memory instead of an NCCL launch (csrc/peer.cu; NCCL stays where peer
+        # mapping is not available).  (A second overlapped NCCL group for conv_2 / conv_3 was tried: its kernel
+        # cannot get SMs while the SM-filling conv_1 weight-gradient kernel runs, so it only added a launch.)
+        self.peer_allreduce = self._bucket.enable_peer_allreduce()
         self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)       # being reduced this step
         self._max_w_use = None                                                      # reduced last step, used now
 
@@ -448,10 +455,12 @@ class Learner:
 
     def _streams(self):
         if not hasattr(self, "_fork"):
-            self._fork = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device),
+            # s1: operand packs (needed much later: default priority); s2: the target network's pass — as critical
+            # as the main branch (both feed the target kernel), so it gets the main branch's priority in the graph
+            self._fork = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device, priority=-2),
                           torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event())
             self._ev_pk, self._ev_tg, self._ev_upd = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-            self._ev_hp = torch.cuda.Event()
+            self._ev_hp, self._ev_mw = torch.cuda.Event(), torch.cuda.Event()
         return self._fork
 
     def _pack_conv1(self):
@@ -480,6 +489,9 @@ class Learner:
                 with self.model.packed_heads_cache():
                     self.model.prepack_heads()
                     self._head_packs = dict(self.model._pack_cache)
+                with self.target_model.packed_heads_cache():      # was ~11 us in front of the target pass's GEMM
+                    self.target_model.prepack_heads()
+                    self._head_packs_tg = dict(self.target_model._pack_cache)
                 self._ev_hp.record(s2)
         return self._ev_pk
 
@@ -494,6 +506,7 @@ class Learner:
         issued here, behind their weight gradients on the sink's lane, while the conv stack's backward still runs."""
         st = self.memory.store
         w_on = getattr(self.model, self._conv_name).conv_1.weight
+        notdone = None
         if packs_done is None:
             self._pack_conv1()
         else:
@@ -529,9 +542,15 @@ class Learner:
                 s2.wait_event(e0)
                 with torch.no_grad():
                     with torch.cuda.stream(s2):
-                        qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
+                        with self.target_model.packed_heads_cache():
+                            if early_packs:
+                                self.target_model._pack_cache.update(self._head_packs_tg)
+                            qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
                         e2.record(s2)
                     with torch.cuda.stream(s1):
+                        if action.dtype != torch.int64:            # int32 replay field -> the target kernel's int64:
+                            action = action.to(torch.int64)        # off the main branch (it sat in front of conv_1)
+                        notdone = 1.0 - done.to(torch.float32)     # likewise (two launches in front of the target kernel)
                         self.model.prepack_heads(transposed=True)   # W^T operand of the heads' dgrad, off the main branch
                         e1.record(s1)
                     y_both = big[0:2].view(2 * B, 20, 20, c_out).permute(0, 3, 1, 2)     # logical NCHW, physical NHWC
@@ -574,7 +593,8 @@ class Learner:
                     qn_target = self.target_model.forward_from_conv1(y_tg, True)[0]  # :85
                 y = _Conv1Gathered.apply(w_on, st.field_view("state"), idx, self._pack1, self._mf, st, None, True)
                 q = self.model.forward_from_conv1(y, True)[0]                        # :78 (ReLU in the conv_1 epilogue)
-        notdone = 1.0 - done.to(torch.float32)
+        if notdone is None:
+            notdone = 1.0 - done.to(torch.float32)
         out = R.apex_target(q.detach(), qn_online, qn_target, action, reward, notdone, weight,
                             self.gamma_n, self.cfg.ALPHA)
         if update_tree:      # priority write-back (one CTA) next to backward instead of after the optimizer
@@ -592,17 +612,23 @@ class Learner:
                 getattr(self.model, self._conv_name).split_backward = True
                 if self._world > 1:
                     self._bucket.attach_sink(self._sink)
-                # Learner.step (:123-138) has no clipping: a parameter can be stepped once its own gradient is final.
-                # At world size 1 the heads (97 % of the elements) are final ~150 us before the conv stack's.
+                # Learner.step (:123-138) has no clipping: a parameter can be stepped once its own gradient is final
+                # (after its all-reduce when data parallel).  The heads (97 % of the elements) are final ~150 us
+                # before the conv stack's.
                 self._early_params = [p for n, p in self.model.named_parameters()
                                       if not n.startswith(self._conv_name + ".")]
-                self._early_ok = (self._world == 1 and self.cfg.EARLY_HEAD_UPDATE and bool(self._early_params)
+                self._early_ok = (self.cfg.EARLY_HEAD_UPDATE and bool(self._early_params)
                                   and self.optim.set_early(self._early_params))
             with self._sink.active():
                 q.backward(out["grad_q"])
             if early_update and self._early_ok and \
                     all(id(p) in self._sink.accumulated[0] for p in self._early_params):
-                self._sink.run_on_lane(self.optim.step_early, 0)
+                if self._world > 1:
+                    # data parallel: the heads' all-reduce was launched from this lane when their last gradient
+                    # landed; the lane waits for it, then steps them — still beside the conv stack's backward
+                    self._sink.run_on_lane(lambda: self._bucket.wait_group(0) and self.optim.step_early(), 0)
+                else:
+                    self._sink.run_on_lane(self.optim.step_early, 0)
             self._sink.join()
         else:
             q.backward(out["grad_q"])
@@ -645,7 +671,9 @@ class Learner:
                 st.sample_fetch(B, self.cfg.BETA, c["idx"], c["w"], {k: c[k] for k in ("action", "reward", "done")},
                                 max_w=max_w)
                 idx = c["idx"]
-                out = self._forward_backward_fused(idx, c["action"].to(torch.int64), c["reward"], c["done"], c["w"],
+                batched = self.cfg.PARALLEL_FORWARDS and self.cfg.BATCHED_ONLINE      # converts the action itself
+                out = self._forward_backward_fused(idx, c["action"] if batched else c["action"].to(torch.int64),
+                                                   c["reward"], c["done"], c["w"],
                                                    packs_done=packs_done, update_tree=side, early_update=True)
             else:
                 idx, _, w = st.sample(B, beta=self.cfg.BETA, want_prob=False, max_w=max_w)
@@ -658,8 +686,14 @@ class Learner:
             else:
                 st.update(idx, out["prio"])
             if mw_work is not None:
-                mw_work.wait()
-                self._max_w_use.copy_(self._max_w)
+                # the reduced maximum becomes the NEXT step's normaliser: wait + copy on a side stream (this step's
+                # draw has long read the old value), joined here at no cost instead of 5 us at the end of the step
+                s1 = self._streams()[0]
+                with torch.cuda.stream(s1):
+                    mw_work.wait()
+                    self._max_w_use.copy_(self._max_w)
+                    self._ev_mw.record(s1)
+                torch.cuda.current_stream(self.device).wait_event(self._ev_mw)
             return {"scalars": out["scalars"], "p_norm": info["p_norm"], "prio": out["prio"], "idx": idx}
 
         lib = st.lib

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2rl.so")
-SOURCES = ["capi.cu", "tree.cu", "gather.cu", "targets.cu", "conv1.cu", "conv1_wgrad.cu", "optim.cu", "gemm.cu", "dueling.cu"]
+SOURCES = ["capi.cu", "tree.cu", "gather.cu", "targets.cu", "conv1.cu", "conv1_wgrad.cu", "optim.cu", "gemm.cu", "dueling.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -23,7 +23,9 @@ class FlatGradBucket:
     def __init__(self, params, device=None):
         self.params = list(params)
         device = device or self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=device, dtype=self.params[0].dtype)
+        total = sum(p.numel() for p in self.params)
+        self._flat_padded = torch.zeros((total + 3) // 4 * 4, device=device, dtype=self.params[0].dtype)
+        self.flat = self._flat_padded[:total]
         off = 0
         for p in self.params:
             # same element order as the parameter (channels_last conv weights keep their strides), so that
@@ -46,29 +48,38 @@ class FlatGradBucket:
 
     # -- overlap: reduce the gradients that are ready EARLY in the backward pass (the big head
     #    matrices, 97 % of the bytes) while the backward of the convolution stack still runs ----
-    def enable_overlap(self, early_params) -> None:
-        """`early_params`: parameters whose gradients are complete first (must be a prefix or any
-        subset; they are moved to the front of the bucket).  Their all-reduce is launched from a
-        post-accumulate hook on the LAST of them; call finish() after backward."""
-        early = [p for p in self.params if any(p is q for q in early_params)]
-        late = [p for p in self.params if not any(p is q for q in early_params)]
-        self.params = early + late
+    def enable_overlap(self, early_params, mid_params=()) -> None:
+        """`early_params`: parameters whose gradients are complete first (the dense heads); `mid_params`: a second
+        group that completes later but still well before the end of backward (conv_2 / conv_3: their weight
+        gradients run on the sink's second lane) — each group is all-reduced as soon as its LAST gradient is
+        reported, so only what is left (conv_1, 32 KB) is reduced after backward.  The bucket is re-laid
+        early | mid | late; call finish() after backward."""
+        def pick(sel):
+            return [p for p in self.params if any(p is q for q in sel)]
+        early, mid = pick(early_params), pick(mid_params)
+        late = [p for p in self.params if not any(p is q for q in early + mid)]
+        self.params = early + mid + late
         off = 0
         for p in self.params:                       # re-lay the bucket: early params first
             p.grad = self.flat[off:off + p.numel()].as_strided(p.shape, p.stride())
             off += p.numel()
-        n_early = sum(p.numel() for p in early)
-        self._early, self._late = self.flat[:n_early], self.flat[n_early:]
-        self._pending, self._work = len(early), None
-        self._ready = set()                 # ids of the early params whose gradient is complete this step
-        self._sink_attached = False
+        n_early, n_mid = sum(p.numel() for p in early), sum(p.numel() for p in mid)
+        self._early, self._late = self.flat[:n_early], self.flat[n_early + n_mid:]
         gloo = dist.is_initialized() and dist.get_backend() != "nccl"
+        # one record per overlapped group: its slice, its parameters, the ids reported this step, the async work
+        self._groups = [dict(flat=f, params=ps, ready=set(), work=None, div=False)
+                        for f, ps in ((self._early, early), (self.flat[n_early:n_early + n_mid], mid)) if ps]
+        self._group_of = {id(p): g for g in self._groups for p in g["params"]}
+        self._sink_attached = False
 
         def mark(p):
-            self._ready.add(id(p))          # a set: a parameter reported twice still counts once
-            if len(self._ready) == self._pending and self._work is None and world() > 1:
-                self._work = self._reduce(self._early, async_op=True)
-                self._early_needs_div = gloo
+            g = self._group_of.get(id(p))
+            if g is None:
+                return
+            g["ready"].add(id(p))           # a set: a parameter reported twice still counts once
+            if len(g["ready"]) == len(g["params"]) and g["work"] is None and world() > 1:
+                g["work"] = self._reduce(g["flat"], async_op=True)
+                g["div"] = gloo
 
         def autograd_hook(p):
             # torch >= 2.x runs post-accumulate-grad hooks even when a custom Function returned None for the
@@ -78,33 +89,130 @@ class FlatGradBucket:
             if not self._sink_attached:
                 mark(p)
 
-        self._early_hook, self._early_params = mark, early
-        for p in early:
+        self._early_hook, self._early_params = mark, early + mid
+        for p in early + mid:
             p.register_post_accumulate_grad_hook(autograd_hook)
+
+    # the first group's handle under its old name (tests and diagnostics read it)
+    @property
+    def _work(self):
+        gs = getattr(self, "_groups", [])
+        return gs[0]["work"] if gs else None
+
+    def enable_peer_allreduce(self) -> bool:
+        """Reduce the late slice (what is left after backward: the critical-path collective) with libb2rl's
+        peer-memory kernel instead of NCCL.  The slice is taken to the end of the bucket, which is padded to a
+        multiple of 4 floats at construction.  Returns False (NCCL stays) where PeerAllReduce is not available."""
+        if not hasattr(self, "_late") or not self._late.numel() or not PeerAllReduce.available(self.flat.device):
+            return False
+        if self._late.numel() > (1 << 20):                  # every rank reads world x slice: a small-message design
+            return False
+        start = self.flat.numel() - self._late.numel()
+        start -= start % 4                                  # 16-byte aligned start: may take in the tail of a group
+        self._late_padded = self._flat_padded[start:]       # ... whose own all-reduce completed before finish()
+        try:
+            self._peer = PeerAllReduce(self._late_padded.numel(), self.flat.device)
+        except Exception as e:                              # no VMM / fabric support on this box: keep NCCL, loudly
+            import warnings
+            warnings.warn(f"peer-memory all-reduce unavailable ({e!r}); the late gradient slice stays on NCCL")
+            self._peer = None
+        return self._peer is not None
 
     def attach_sink(self, sink) -> None:
         """Weight gradients that bypass autograd's AccumulateGrad (linear.WeightGradSink) report here instead:
-        the early all-reduce is then launched from the sink's side stream as soon as the last early gradient
+        a group's all-reduce is then launched from the sink's side stream as soon as its last gradient
         has been accumulated there."""
         self._sink_attached = True
         for p in getattr(self, "_early_params", []):
             sink.on_ready[id(p)] = self._early_hook
 
+    def wait_group(self, i: int = 0) -> bool:
+        """Make the CURRENT stream wait for group i's all-reduce (launched by the hooks) and finish its mean.
+        True if the group had been launched — its gradients are then final on this stream (the early optimizer
+        step of the heads uses this); finish() will not wait for it again."""
+        gs = getattr(self, "_groups", [])
+        if i >= len(gs) or gs[i]["work"] is None:
+            return False
+        g = gs[i]
+        if g["work"] is not True:
+            g["work"].wait()
+            if g["div"]:
+                g["flat"].div_(world())
+            g["work"] = True                # done: finish() will not wait again
+        return True
+
     def finish(self) -> None:
-        """After backward: reduce the late (small) part, then wait for the early part."""
+        """After backward: reduce the late (small) part, then wait for the overlapped groups."""
+        gs = getattr(self, "_groups", [])
         if world() == 1:
-            self._ready.clear() if hasattr(self, "_ready") else None
+            for g in gs:
+                g["ready"].clear()
             return
         if self._late.numel():
-            self._reduce(self._late)
-        if self._work is not None:
-            self._work.wait()
-            if getattr(self, "_early_needs_div", False):
-                self._early.div_(world())
-        else:                                       # hooks did not fire (no early grads): reduce now
-            self._reduce(self._early)
-        self._work = None
-        self._ready.clear()
+            if getattr(self, "_peer", None) is not None:
+                self._peer.mean_(self._late_padded)          # one kernel over NVLink peer memory (csrc/peer.cu)
+            else:
+                self._reduce(self._late)
+        for i, g in enumerate(gs):
+            if g["work"] is None:                   # hooks did not fire (no such grads this step): reduce now
+                self._reduce(g["flat"])
+            else:
+                self.wait_group(i)
+            g["work"] = None
+            g["ready"].clear()
+
+
+class PeerAllReduce:
+    """libb2rl's one-kernel mean all-reduce over NVLink peer memory (csrc/peer.cu) for ONE fixed slice size.
+    Staging buffers and flag pads are torch symmetric-memory allocations (CUDA VMM handles exchanged through the
+    process group's store), so every rank holds device pointers into every peer.  `available()` is False — and
+    the caller keeps NCCL — off NCCL, across nodes, or when the rendezvous fails."""
+
+    def __init__(self, n: int, device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.n = int(n)
+        assert self.n % 4 == 0 and self.n >= 4
+        self.device = torch.device(device)
+        L = _lib.load()
+        ctas = int(L.b2rl_peer_allreduce_max_ctas())
+        w = world()
+        group = dist.group.WORLD
+        self.stage = symm.empty(2 * self.n, dtype=torch.float32, device=self.device)
+        self.flags = symm.empty(w * ctas, dtype=torch.int32, device=self.device)
+        self.flags.zero_()
+        self.stage.zero_()
+        torch.cuda.synchronize(self.device)
+        hs, hf = symm.rendezvous(self.stage, group), symm.rendezvous(self.flags, group)
+        self.rank, self.world = int(hs.rank), int(hs.world_size)
+        self._stage_ptrs = torch.tensor(list(hs.buffer_ptrs), dtype=torch.int64, device=self.device)
+        self._flag_ptrs = torch.tensor(list(hf.buffer_ptrs), dtype=torch.int64, device=self.device)
+        self._epoch = torch.zeros(ctas, dtype=torch.int32, device=self.device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._handles = (hs, hf)
+        dist.barrier()                     # every pad is zeroed before any rank's first flag can land
+
+    def mean_(self, t: torch.Tensor) -> torch.Tensor:
+        """In place: t <- mean over ranks of t (t: contiguous fp32, numel == n, 16-byte aligned)."""
+        assert t.numel() == self.n and t.is_contiguous() and t.dtype == torch.float32
+        self._lib.check(self._lib.load().b2rl_peer_allreduce_mean(
+            self._stage_ptrs.data_ptr(), self._flag_ptrs.data_ptr(), self.rank, self.world, self.n, t.data_ptr(),
+            self.n, self._epoch.data_ptr(), self.error.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream))
+        return t
+
+    @staticmethod
+    def available(device) -> bool:
+        import os
+        if os.environ.get("B2RL_NO_PEER_ALLREDUCE") or not dist.is_initialized() or dist.get_backend() != "nccl":
+            return False
+        if world() < 2 or world() > 16 or torch.device(device).type != "cuda":
+            return False
+        # one node only: every rank must see every other rank's GPU as a peer
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", world()))
+        return local == world() and torch.cuda.device_count() >= world()
 
 
 def all_reduce_max_(x: torch.Tensor, async_op: bool = False):

@@ -325,6 +325,21 @@ int b2rl_dueling_backward_w(const float* h_dev, const float* row_ws_dev, int64_t
  * `gpu_launches`). */
 int64_t b2rl_launch_count(void);
 
+/* Replay-sharded data parallelism (the reference has one learner process and no collective:
+ * APE_X/Learner.py:123-138 steps a single model).  Mean all-reduce of the SMALL gradient slice that is left when
+ * backward ends (the convolution stack: 0.3 MB) across the learner ranks of one node, as one kernel per rank over
+ * NVLink / NVSwitch peer memory: stage -> per-CTA flag to every peer -> read every rank's staged slice through the
+ * peer mapping, add in rank order (bit-identical on all ranks), scale, write data_dev in place.
+ * stage_ptrs_dev / flag_ptrs_dev: DEVICE arrays of `world` device pointers — rank r's staging buffer
+ * (2 * stage_cap_floats floats) and flag pad (world * b2rl_peer_allreduce_max_ctas() uint32, zeroed once), both
+ * mapped into this process (CUDA IPC / VMM; the Python host uses torch symmetric memory).  epoch_dev:
+ * max_ctas uint32 zeroed once, private to the rank; error_dev: set to 1 if a peer never arrived (bounded spin).
+ * Every rank must call it the same number of times with the same n. */
+int32_t b2rl_peer_allreduce_max_ctas(void);
+int b2rl_peer_allreduce_mean(const uint64_t* stage_ptrs_dev, const uint64_t* flag_ptrs_dev, int32_t rank,
+                             int32_t world, int64_t stage_cap_floats, float* data_dev, int64_t n,
+                             uint32_t* epoch_dev, uint32_t* error_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

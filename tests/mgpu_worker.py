@@ -97,6 +97,17 @@ def main():
         if r > 1e-5:
             bad.append(f"{n}: vs mean {r:.3e}, vs own shard {rel(a, own):.3e}, vs sum {rel(a, b):.3e}")
     assert not bad, "rank %d: %s" % (rank, "; ".join(bad))
+    # the late slice (conv stack) goes through libb2rl's peer-memory kernel when the ranks share a node: it sums in
+    # rank order, so every rank must hold BIT-identical averaged gradients, and no peer may have timed out
+    peer = bool(getattr(L, "peer_allreduce", False))
+    if peer:
+        late = L._bucket._late.clone()
+        every = [torch.empty_like(late) for _ in range(world)]
+        dist.all_gather(every, late)
+        assert all(torch.equal(every[0], e) for e in every), "peer all-reduce: ranks disagree bitwise"
+        assert int(L._bucket._peer.error.item()) == 0
+    elif not os.environ.get("B2RL_NO_PEER_ALLREDUCE"):
+        raise AssertionError("peer-memory all-reduce expected on a single-node NCCL run")
 
     # ---- step loop: the IS-weight normaliser is the MAX reduced during the previous step ------------------
     st = L.memory.store
@@ -119,7 +130,9 @@ def main():
         assert rel(w, w_exp) <= 1e-6, (k, rel(w, w_exp))
         assert float(L._max_w_use) == float(gm)                      # reduced behind this step, used by the next
         prev_use = float(gm)
-    print(f"MGPU_OK rank {rank}/{world} worst_grad_rel {worst:.2e}", flush=True)
+    if peer:
+        assert int(L._bucket._peer.error.item()) == 0
+    print(f"MGPU_OK rank {rank}/{world} worst_grad_rel {worst:.2e} peer_allreduce {peer}", flush=True)
     dist.barrier()
     torch.cuda.synchronize()
     dist.destroy_process_group()

@@ -107,6 +107,27 @@ def _worker(rank, world, port, q):
     mean_b = sum(float(2 * r + 1) for r in range(world)) / world
     out["none_grad_hooks_ok"] = (not started_early) and (not after_one) and \
         bool(torch.allclose(wa.grad, torch.full_like(wa, mean_a))) and bool(torch.allclose(wb.grad, torch.full_like(wb, mean_b)))
+    # 1e. two overlapped groups (heads | conv_2, conv_3) + a late rest (conv_1), reported through the sink in the
+    #     order the learner's two lanes do; wait_group(0) (the early optimizer step's gate) finishes group 0 alone
+    ws = [torch.nn.Parameter(torch.randn(3, 3)) for _ in range(5)]
+    b5 = D.FlatGradBucket(ws)
+    b5.enable_overlap([ws[3], ws[4]], [ws[1], ws[2]])
+
+    class _Sink5:
+        on_ready = {}
+    b5.attach_sink(_Sink5)
+    gs5 = [torch.full((3, 3), float((i + 1) * (rank + 1))) for i in range(5)]
+    gate_before = b5.wait_group(0)
+    for i in (4, 3):                                     # heads' lane
+        ws[i].grad.add_(gs5[i]); _Sink5.on_ready[id(ws[i])](ws[i])
+    gate_after = b5.wait_group(0)
+    heads_final = all(bool(torch.allclose(ws[i].grad, torch.full((3, 3), (i + 1) * (world + 1) / 2.0))) for i in (3, 4))
+    for i in (2, 1):                                     # conv lane
+        ws[i].grad.add_(gs5[i]); _Sink5.on_ready[id(ws[i])](ws[i])
+    ws[0].grad.add_(gs5[0])                              # conv_1: plain late gradient
+    b5.finish()
+    out["two_groups_ok"] = (not gate_before) and gate_after and heads_final and all(
+        bool(torch.allclose(ws[i].grad, torch.full((3, 3), (i + 1) * (world + 1) / 2.0))) for i in range(5))
     # 2. priority-max reduction: shard-local IS weights / global max == single-replay formula
     n, beta = 1024, 0.4
     rng = np.random.default_rng(100 + rank)
@@ -152,6 +173,7 @@ def test_world2_gloo_data_parallel_logic():
         assert res[r]["overlap_ok"], res[r]
         assert res[r]["sink_ok"], res[r]
         assert res[r]["none_grad_hooks_ok"], res[r]
+        assert res[r]["two_groups_ok"], res[r]
     assert res[0]["mw"] == res[1]["mw"]
 
 
