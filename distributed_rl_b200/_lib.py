@@ -55,6 +55,7 @@ SIGNATURES = {
     "b2rl_rmsprop_norm_finish": (C.c_int, [c_vp, c_i32, c_vp, c_vp]),
     "b2rl_peer_allreduce_max_ctas": (c_i32, []),
     "b2rl_peer_allreduce_mean": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "b2rl_peer_allreduce_mean_big": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "b2rl_gemm_packed_floats": (c_i64, [c_i64, c_i64, c_i32]),
     "b2rl_gemm_split_pack": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "b2rl_gemm_split_pack_into": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),

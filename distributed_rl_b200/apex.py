@@ -348,7 +348,8 @@ class Learner:
         from . import dist as D
         self._D = D
         self._world = D.world()
-        self._bucket = D.FlatGradBucket(self.model.getParameters(), self.device)
+        self._bucket = D.FlatGradBucket(self.model.getParameters(), self.device,
+                                        symmetric=D.PeerAllReduce.available(self.device))
         # the dense heads hold 97 % of the parameters and their gradients are complete first in the
         # backward pass: their all-reduce overlaps the backward of the convolution stack
         import os
@@ -361,6 +362,7 @@ class Learner:
         # mapping is not available).  (A second overlapped NCCL group for conv_2 / conv_3 was tried: its kernel
         # cannot get SMs while the SM-filling conv_1 weight-gradient kernel runs, so it only added a launch.)
         self.peer_allreduce = self._bucket.enable_peer_allreduce()
+        self.peer_allreduce_heads = getattr(self._bucket, "_peer_big", None) is not None
         self._max_w = torch.empty(1, dtype=torch.float32, device=self.device)       # being reduced this step
         self._max_w_use = None                                                      # reduced last step, used now
 

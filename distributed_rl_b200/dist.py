@@ -20,11 +20,27 @@ def world() -> int:
 class FlatGradBucket:
     """All gradients of `params` as views into ONE contiguous buffer -> one collective per step."""
 
-    def __init__(self, params, device=None):
+    def __init__(self, params, device=None, symmetric: bool = False):
+        """symmetric=True: the bucket is a torch symmetric-memory allocation (every rank can map every other rank's
+        bucket), which lets libb2rl's peer-memory all-reduce read the peers' gradients in place (csrc/peer.cu)."""
         self.params = list(params)
         device = device or self.params[0].device
         total = sum(p.numel() for p in self.params)
-        self._flat_padded = torch.zeros((total + 3) // 4 * 4, device=device, dtype=self.params[0].dtype)
+        padded = (total + 3) // 4 * 4
+        self._symm = None
+        if symmetric:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                self._flat_padded = symm.empty(padded, dtype=self.params[0].dtype, device=device)
+                self._flat_padded.zero_()
+                torch.cuda.synchronize(device)
+                self._symm = symm.rendezvous(self._flat_padded, dist.group.WORLD)
+            except Exception as e:                              # keep NCCL, loudly
+                import warnings
+                warnings.warn(f"symmetric gradient bucket unavailable ({e!r}); all-reduces stay on NCCL")
+                self._symm = None
+        if self._symm is None:
+            self._flat_padded = torch.zeros(padded, device=device, dtype=self.params[0].dtype)
         self.flat = self._flat_padded[:total]
         off = 0
         for p in self.params:
@@ -78,8 +94,13 @@ class FlatGradBucket:
                 return
             g["ready"].add(id(p))           # a set: a parameter reported twice still counts once
             if len(g["ready"]) == len(g["params"]) and g["work"] is None and world() > 1:
-                g["work"] = self._reduce(g["flat"], async_op=True)
-                g["div"] = gloo
+                big = getattr(self, "_peer_big", None)
+                if big is not None and g is self._groups[0]:
+                    big.mean_()                 # one libb2rl kernel on THIS stream (reduce-scatter + all-gather
+                    g["work"] = True            # over NVLink peer memory): final for whatever follows on the stream
+                else:
+                    g["work"] = self._reduce(g["flat"], async_op=True)
+                    g["div"] = gloo
 
         def autograd_hook(p):
             # torch >= 2.x runs post-accumulate-grad hooks even when a custom Function returned None for the
@@ -110,12 +131,25 @@ class FlatGradBucket:
         start = self.flat.numel() - self._late.numel()
         start -= start % 4                                  # 16-byte aligned start: may take in the tail of a group
         self._late_padded = self._flat_padded[start:]       # ... whose own all-reduce completed before finish()
+        import os
+        import warnings
         try:
             self._peer = PeerAllReduce(self._late_padded.numel(), self.flat.device)
         except Exception as e:                              # no VMM / fabric support on this box: keep NCCL, loudly
-            import warnings
             warnings.warn(f"peer-memory all-reduce unavailable ({e!r}); the late gradient slice stays on NCCL")
             self._peer = None
+        # the early group (dense heads) in place in the symmetric bucket: reduce-scatter + all-gather kernel
+        self._peer_big = None
+        gs = getattr(self, "_groups", [])
+        if self._peer is not None and self._symm is not None and gs and gs[0]["flat"].numel() % 4 == 0 \
+                and gs[0]["flat"].data_ptr() == self._flat_padded.data_ptr() \
+                and os.environ.get("B2RL_PEER_ALLREDUCE_BIG"):
+            # opt-in: correct (tests/mgpu_worker.py), but at 2 ranks the kernel took 111 us against NCCL's 63 us
+            # running beside backward at the lane's low priority (profiles/r02_timeline_2gpu.txt)
+            try:
+                self._peer_big = PeerAllReduceBig(self._symm, gs[0]["flat"].numel(), self.flat.device)
+            except Exception as e:
+                warnings.warn(f"peer-memory all-reduce of the heads unavailable ({e!r}); they stay on NCCL")
         return self._peer is not None
 
     def attach_sink(self, sink) -> None:
@@ -213,6 +247,43 @@ class PeerAllReduce:
         # one node only: every rank must see every other rank's GPU as a peer
         local = int(os.environ.get("LOCAL_WORLD_SIZE", world()))
         return local == world() and torch.cuda.device_count() >= world()
+
+
+class PeerAllReduceBig:
+    """libb2rl's reduce-scatter + all-gather kernel (csrc/peer.cu k_peer_allreduce_big) over the first `n` floats of a
+    symmetric gradient bucket (`handle`: its rendezvous).  mean_() leaves the rank-ordered mean in every rank's
+    bucket, bit-identical across ranks, as ONE launch on the current stream."""
+
+    CTAS = 32
+
+    def __init__(self, handle, n: int, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._lib = _lib
+        self.device = torch.device(device)
+        self.n = int(n)
+        self.rank, self.world = int(handle.rank), int(handle.world_size)
+        self.slice = (self.n + 4 * self.world - 1) // (4 * self.world) * 4
+        L = _lib.load()
+        ctas = int(L.b2rl_peer_allreduce_max_ctas())
+        self.result = symm.empty(2 * self.slice, dtype=torch.float32, device=self.device)
+        self.flags = symm.empty(2 * self.world * ctas, dtype=torch.int32, device=self.device)
+        self.result.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize(self.device)
+        hr, hf = symm.rendezvous(self.result, dist.group.WORLD), symm.rendezvous(self.flags, dist.group.WORLD)
+        mk = lambda ptrs: torch.tensor(list(ptrs), dtype=torch.int64, device=self.device)   # noqa: E731
+        self._bucket_ptrs, self._result_ptrs, self._flag_ptrs = mk(handle.buffer_ptrs), mk(hr.buffer_ptrs), mk(hf.buffer_ptrs)
+        self._epoch = torch.zeros(ctas, dtype=torch.int32, device=self.device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._handles = (handle, hr, hf)
+        dist.barrier()
+
+    def mean_(self) -> None:
+        self._lib.check(self._lib.load().b2rl_peer_allreduce_mean_big(
+            self._bucket_ptrs.data_ptr(), self._result_ptrs.data_ptr(), self._flag_ptrs.data_ptr(), self.rank,
+            self.world, self.n, self.slice, self.CTAS, self._epoch.data_ptr(), self.error.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream))
 
 
 def all_reduce_max_(x: torch.Tensor, async_op: bool = False):

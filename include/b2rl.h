@@ -339,6 +339,16 @@ int32_t b2rl_peer_allreduce_max_ctas(void);
 int b2rl_peer_allreduce_mean(const uint64_t* stage_ptrs_dev, const uint64_t* flag_ptrs_dev, int32_t rank,
                              int32_t world, int64_t stage_cap_floats, float* data_dev, int64_t n,
                              uint32_t* epoch_dev, uint32_t* error_dev, void* stream);
+/* The LARGE slice (the dense heads' 12.9 MB, cfg/ape_x.json:52-71) as reduce-scatter + all-gather in one kernel:
+ * the gradient bucket itself is peer-mapped (bucket_ptrs_dev[r] = rank r's slice start, n floats); rank r reduces
+ * floats [r * slice_floats, ...) of every rank's bucket in rank order into its own bucket and into its result buffer
+ * (result_ptrs_dev[r]: 2 * slice_floats floats), then gathers every peer's result.  Flag pads: 2 * world * max_ctas
+ * uint32 per rank, zeroed once.  `ctas` CTAs (<= max_ctas, the same on every rank); launched on the stream that
+ * produced the gradients, it overlaps the rest of backward (new work, no reference counterpart). */
+int b2rl_peer_allreduce_mean_big(const uint64_t* bucket_ptrs_dev, const uint64_t* result_ptrs_dev,
+                                 const uint64_t* flag_ptrs_dev, int32_t rank, int32_t world, int64_t n,
+                                 int64_t slice_floats, int32_t ctas, uint32_t* epoch_dev, uint32_t* error_dev,
+                                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,15 @@ def main():
         dist.all_gather(every, late)
         assert all(torch.equal(every[0], e) for e in every), "peer all-reduce: ranks disagree bitwise"
         assert int(L._bucket._peer.error.item()) == 0
+        big = L._bucket._peer_big
+        if big is not None:                                   # the heads: reduce-scatter + all-gather kernel
+            heads = L._bucket._early.clone()
+            every = [torch.empty_like(heads) for _ in range(world)]
+            dist.all_gather(every, heads)
+            assert all(torch.equal(every[0], e) for e in every), "peer all-reduce (heads): ranks disagree bitwise"
+            assert int(big.error.item()) == 0
+        elif os.environ.get("B2RL_PEER_ALLREDUCE_BIG"):
+            raise AssertionError("peer-memory all-reduce of the heads was requested but is not active")
     elif not os.environ.get("B2RL_NO_PEER_ALLREDUCE"):
         raise AssertionError("peer-memory all-reduce expected on a single-node NCCL run")
 
@@ -132,7 +141,7 @@ def main():
         prev_use = float(gm)
     if peer:
         assert int(L._bucket._peer.error.item()) == 0
-    print(f"MGPU_OK rank {rank}/{world} worst_grad_rel {worst:.2e} peer_allreduce {peer}", flush=True)
+    print(f"MGPU_OK rank {rank}/{world} worst_grad_rel {worst:.2e} peer_allreduce {peer} heads {bool(peer and L._bucket._peer_big is not None)}", flush=True)
     dist.barrier()
     torch.cuda.synchronize()
     dist.destroy_process_group()
