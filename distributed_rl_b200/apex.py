@@ -480,21 +480,22 @@ class Learner:
         self._ev_pk.record(cur)
         s1.wait_event(self._ev_pk)
         s2.wait_event(self._ev_pk)
-        with torch.cuda.stream(s1):
+        with torch.cuda.stream(s2):          # the high-priority side stream: conv_1 waits for these three launches
             self._pack_conv1()
-            self._ev_pk.record(s1)
-        # The heads' forward operand (two 3136 x 512 matrices -> one packed image) is needed ~150 us into the step:
-        # built on the second side stream now instead of on the main branch in front of conv_1.
+            self._ev_pk.record(s2)
+        # The heads' forward operands (online and target: four 3136 x 512 matrices -> two packed images) are needed
+        # ~120 us into the step: built on the low-priority side stream now instead of on the main / target branches
+        # in front of their GEMMs.
         self._head_packs = None
         if self.cfg.PARALLEL_FORWARDS and self.cfg.BATCHED_ONLINE:
-            with torch.cuda.stream(s2):
+            with torch.cuda.stream(s1):
                 with self.model.packed_heads_cache():
                     self.model.prepack_heads()
                     self._head_packs = dict(self.model._pack_cache)
                 with self.target_model.packed_heads_cache():      # was ~11 us in front of the target pass's GEMM
                     self.target_model.prepack_heads()
                     self._head_packs_tg = dict(self.target_model._pack_cache)
-                self._ev_hp.record(s2)
+                self._ev_hp.record(s1)
         return self._ev_pk
 
     def _forward_backward_fused(self, idx, action, reward, done, weight, packs_done=None, update_tree=False,
@@ -526,7 +527,7 @@ class Learner:
                 cur = torch.cuda.current_stream(self.device)
                 early_packs = packs_done is not None and bool(getattr(self, "_head_packs", None))
                 if early_packs:
-                    self.model._pack_cache.update(self._head_packs)       # built on s2 at the start of the step
+                    self.model._pack_cache.update(self._head_packs)       # built on s1 at the start of the step
                 else:
                     self.model.prepack_heads()
                 B = idx.numel()
