@@ -47,6 +47,8 @@ SIGNATURES = {
                          + [c_vp] * 6),
     "b2rl_vtrace": (C.c_int, [c_vp] * 5 + [c_i32, c_i32, c_f32, c_f32, c_f32, c_f32] + [c_vp] * 3),
     "b2rl_conv1_pack": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "b2rl_conv1_pack_jobs": (C.c_int, [C.POINTER(c_vp), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_vp),
+                                       C.POINTER(c_vp), c_i32, c_i32, c_vp]),
     "b2rl_conv1_fused": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),
     "b2rl_conv1_wgrad_workspace_floats": (c_i64, [c_i32]),
     "b2rl_conv1_wgrad": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp]),

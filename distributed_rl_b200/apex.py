@@ -284,6 +284,7 @@ class _Conv1Gathered(torch.autograd.Function):
         """relu=True: the kernel's epilogue applies the ReLU that follows conv_1 and backward applies its mask
         inside the wgrad kernel (the caller must then skip the network's own ReLU: forward_from_conv1(y, True))."""
         ctx.frames, ctx.store, ctx.mem_format, ctx.wshape = frames, store, mem_format, weight.shape
+        ctx.weight_param = weight
         ctx.has_idx, ctx.relu = idx is not None, bool(relu)
         idx_t = idx if idx is not None else torch.empty(0, dtype=torch.int64, device=frames.device)
         if y_pre is not None:
@@ -302,6 +303,13 @@ class _Conv1Gathered(torch.autograd.Function):
         y = ctx.saved_tensors[1] if ctx.relu else None
         if _Conv1Gathered.fused_wgrad:
             # fused gather + wgrad on the tensor cores: the sampled rows are never staged (csrc/conv1_wgrad.cu)
+            w = ctx.weight_param
+            from . import linear as _lin
+            if _lin._SINK is not None and w.grad is not None and w.grad.is_contiguous():
+                # deferred-gradient mode (grads pre-allocated, zeroed by the optimizer): the kernel's reduction adds
+                # straight into .grad — no temporary, no AccumulateGrad launch at the very end of backward
+                R.conv1_wgrad(ctx.frames, idx if ctx.has_idx else None, gy, out=w.grad, accumulate=True, relu_y=y)
+                return (None,) * len(ctx.needs_input_grad)
             gw = R.conv1_wgrad(ctx.frames, idx if ctx.has_idx else None, gy, relu_y=y)
             return (gw,) + (None,) * (len(ctx.needs_input_grad) - 1)
         if y is not None:
@@ -468,9 +476,7 @@ class Learner:
     def _pack_conv1(self):
         w_on = getattr(self.model, self._conv_name).conv_1.weight
         w_tg = getattr(self.target_model, self._conv_name).conv_1.weight
-        self._pack1.pack(0, w_on)
-        self._pack2.pack(0, w_on)
-        self._pack2.pack(1, w_tg)
+        R.conv1_pack_jobs([(self._pack1, 0, w_on), (self._pack2, 0, w_on), (self._pack2, 1, w_tg)])   # one launch
 
     def _pack_conv1_async(self):
         """The conv_1 weight packs of this step on a side stream (they only depend on the weights): they overlap

@@ -139,11 +139,10 @@ __host__ __device__ __forceinline__ int sw128_offset(int rows, int n, int k) {
 }
 
 // ---- weight packing: fp32 [32][256] -> 4 signed 7-bit digits per weight, per-channel scale ----
-__global__ void __launch_bounds__(K_TOTAL)
-k_conv1_pack(const float* __restrict__ w, int net, int n_nets, int c_out, int8_t* __restrict__ bq,
-             float* __restrict__ scale) {
+__device__ __forceinline__ void pack_channel(const float* __restrict__ w, int net, int n_nets, int c_out, int co,
+                                             int8_t* __restrict__ bq, float* __restrict__ scale) {
   __shared__ float s_max[K_TOTAL / 32];
-  const int co = blockIdx.x, k = threadIdx.x;
+  const int k = threadIdx.x;
   const float v = w[co * K_TOTAL + k];
   float m = fabsf(v);
 #pragma unroll
@@ -163,6 +162,27 @@ k_conv1_pack(const float* __restrict__ w, int net, int n_nets, int c_out, int8_t
     bq[sw128_offset(rows, net * NSPLIT * c_out + j * c_out + co, k)] = (int8_t)q;
     x = (x - q) * 128.0;
   }
+}
+
+__global__ void __launch_bounds__(K_TOTAL)
+k_conv1_pack(const float* __restrict__ w, int net, int n_nets, int c_out, int8_t* __restrict__ bq,
+             float* __restrict__ scale) {
+  pack_channel(w, net, n_nets, c_out, blockIdx.x, bq, scale);
+}
+
+// Several packs in ONE launch (blockIdx.y = job): the learner step packs the online weights for its one-network and
+// its two-network launch and the target weights for the latter — three launches in front of conv_1 became one.
+constexpr int MAX_PACK_JOBS = 4;
+struct PackJobs {
+  const float* w[MAX_PACK_JOBS];
+  int8_t* bq[MAX_PACK_JOBS];
+  float* scale[MAX_PACK_JOBS];
+  int32_t net[MAX_PACK_JOBS], n_nets[MAX_PACK_JOBS];
+};
+__global__ void __launch_bounds__(K_TOTAL)
+k_conv1_pack_jobs(const __grid_constant__ PackJobs J, int c_out) {
+  const int j = blockIdx.y;
+  pack_channel(J.w[j], J.net[j], J.n_nets[j], c_out, blockIdx.x, J.bq[j], J.scale[j]);
 }
 
 struct Params {
@@ -469,6 +489,25 @@ extern "C" int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, 
   B2RL_REQUIRE(c_out == 16 || c_out == 32, "c_out must be 16 or 32");
   conv1::k_conv1_pack<<<c_out, conv1::K_TOTAL, 0, (cudaStream_t)stream>>>(w_dev, net, n_nets, c_out, bq_out_dev,
                                                                          scale_out_dev);
+  count_launch();
+  B2RL_CHECK_LAUNCH();
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_conv1_pack_jobs(const float* const* w_dev, const int32_t* net, const int32_t* n_nets,
+                                    int8_t* const* bq_out_dev, float* const* scale_out_dev, int32_t jobs,
+                                    int32_t c_out, void* stream) {
+  B2RL_REQUIRE(w_dev && net && n_nets && bq_out_dev && scale_out_dev, "null argument");
+  B2RL_REQUIRE(jobs >= 1 && jobs <= conv1::MAX_PACK_JOBS, "1..4 pack jobs");
+  B2RL_REQUIRE(c_out == 16 || c_out == 32, "c_out must be 16 or 32");
+  conv1::PackJobs J{};
+  for (int j = 0; j < jobs; ++j) {
+    B2RL_REQUIRE(w_dev[j] && bq_out_dev[j] && scale_out_dev[j], "null pack job");
+    B2RL_REQUIRE(n_nets[j] >= 1 && n_nets[j] <= 2 && net[j] >= 0 && net[j] < n_nets[j], "n_nets must be 1 or 2");
+    J.w[j] = w_dev[j]; J.bq[j] = bq_out_dev[j]; J.scale[j] = scale_out_dev[j];
+    J.net[j] = net[j]; J.n_nets[j] = n_nets[j];
+  }
+  conv1::k_conv1_pack_jobs<<<dim3(c_out, jobs), conv1::K_TOTAL, 0, (cudaStream_t)stream>>>(J, c_out);
   count_launch();
   B2RL_CHECK_LAUNCH();
   return B2RL_OK;

@@ -423,6 +423,20 @@ class Conv1Pack:
                                           self.scale.data_ptr(), _stream_ptr(self.device)))
 
 
+def conv1_pack_jobs(jobs) -> None:
+    """jobs: up to 4 (pack, net, weight) triples -> ONE launch of all the packs (b2rl_conv1_pack_jobs)."""
+    import ctypes as C
+    n = len(jobs)
+    ws = [w.detach().to(torch.float32).contiguous(memory_format=torch.contiguous_format) for _, _, w in jobs]
+    c_out = jobs[0][0].c_out
+    assert all(p.c_out == c_out and w.shape == (c_out, 4, 8, 8) for (p, _, _), w in zip(jobs, ws))
+    arr = C.c_void_p * n
+    check(_lib.load().b2rl_conv1_pack_jobs(
+        arr(*[w.data_ptr() for w in ws]), (C.c_int32 * n)(*[net for _, net, _ in jobs]),
+        (C.c_int32 * n)(*[p.n_nets for p, _, _ in jobs]), arr(*[p.bq.data_ptr() for p, _, _ in jobs]),
+        arr(*[p.scale.data_ptr() for p, _, _ in jobs]), n, c_out, _stream_ptr(jobs[0][0].device)))
+
+
 def conv1_fused(frames: torch.Tensor, idx, pack: Conv1Pack, relu: bool = False, out=None):
     """frames: uint8 (rows, 4, 84, 84) contiguous (e.g. DeviceReplay.field_view("state"));
     idx: int64[n] rows to take (None: all rows in order).

@@ -239,6 +239,12 @@ int b2rl_vtrace(const float* pi_a_dev, const float* mu_a_dev, const float* value
  *                     [n_nets][n][20][20][c_out] (NHWC), relu != 0 applies ReLU. */
 int b2rl_conv1_pack(const float* w_dev, int32_t net, int32_t n_nets, int32_t c_out, int8_t* bq_out_dev,
                     float* scale_out_dev, void* stream);
+/* Up to 4 such packs in ONE launch (host arrays of `jobs` entries): the learner step packs the online conv_1 weights
+ * for its one-network and its two-network b2rl_conv1_fused launch and the target weights for the latter
+ * (APE_X/Learner.py:78,85,87 evaluate conv_1 with both parameter sets every step). */
+int b2rl_conv1_pack_jobs(const float* const* w_dev, const int32_t* net, const int32_t* n_nets,
+                         int8_t* const* bq_out_dev, float* const* scale_out_dev, int32_t jobs, int32_t c_out,
+                         void* stream);
 int b2rl_conv1_fused(const uint8_t* frames_dev, int64_t capacity, const int64_t* idx_dev, int64_t n,
                      const int8_t* bq_dev, const float* scale_dev, int32_t n_nets, int32_t c_out,
                      float* out_dev, int32_t relu, void* stream);
