@@ -397,7 +397,8 @@ class Learner:
         fusable = (self.cfg.FUSED_OPTIM and info["name"] == "rmsprop" and not info.get("momentum", 0)
                    and not info.get("decay", 0) and self.device.type == "cuda")
         if fusable:
-            from .optim import FusedRMSprop
+            from .optim import FusedRMSprop, flat_grads
+            self._grad_flat = flat_grads(self.model.getParameters())     # adjacent head gradients: see linear._stacked_rows
             self.optim = FusedRMSprop(self.model.getParameters(), lr=info["lr"], alpha=info.get("alpha", 0.99),
                                       eps=info.get("eps", 1e-5), centered=info.get("centered", False))
         else:
@@ -628,6 +629,7 @@ class Learner:
                                       if not n.startswith(self._conv_name + ".")]
                 self._early_ok = (self.cfg.EARLY_HEAD_UPDATE and bool(self._early_params)
                                   and self.optim.set_early(self._early_params))
+            self._sink.grads_are_zero = True      # this branch: grads pre-allocated and zeroed by the fused optimizer
             with self._sink.active():
                 q.backward(out["grad_q"])
             if early_update and self._early_ok and \

@@ -73,6 +73,8 @@ class FlatGradBucket:
         def pick(sel):
             return [p for p in self.params if any(p is q for q in sel)]
         early, mid = pick(early_params), pick(mid_params)
+        early.sort(key=lambda p: -p.numel())        # stable: equally shaped big matrices end up back to back, so one
+        #                                             GEMM can write the sibling heads' gradients (linear._stacked_rows)
         late = [p for p in self.params if not any(p is q for q in early + mid)]
         self.params = early + mid + late
         off = 0

@@ -91,6 +91,22 @@ class FusedRMSprop:
             p.grad.zero_()
 
 
+def flat_grads(params) -> torch.Tensor:
+    """Pre-allocate every .grad as a view into ONE zero buffer, largest tensors first (so equally shaped big matrices —
+    the dense heads' first layers — lie back to back and one GEMM can write all of them: linear._stacked_rows).
+    Each view keeps its parameter's element order.  Returns the buffer."""
+    params = [p for p in params]
+    order = sorted(range(len(params)), key=lambda i: -params[i].numel())
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros((total + 3) // 4 * 4, dtype=params[0].dtype, device=params[0].device)
+    off = 0
+    for i in order:
+        p = params[i]
+        p.grad = flat[off:off + p.numel()].as_strided(p.shape, p.stride())
+        off += p.numel()
+    return flat
+
+
 def _dense(t: torch.Tensor) -> bool:
     """True if t's storage is a dense permutation (contiguous in some dim order)."""
     return t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last) or \

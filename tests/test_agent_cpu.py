@@ -73,3 +73,30 @@ def test_hostmem_cpulist_parsing_and_unbound_fallback():
     with hostmem.on_gpu_node("cuda:0") as bound:               # no GPU here: must be a no-op
         assert bound in (False, True)
     assert os.sched_getaffinity(0) == before
+
+
+def test_flat_grads_lay_sibling_head_gradients_back_to_back():
+    """optim.flat_grads pre-allocates every .grad in one buffer, largest first, so that the two dense heads' first-layer
+    gradients (cfg/ape_x.json:52-71) are consecutive row blocks: linear._stacked_rows then hands the weight-gradient
+    GEMM ONE (1024, 3136) output view.  Reversed or non-adjacent tensors must be refused (the caller falls back to
+    temporaries + add)."""
+    import torch
+    from distributed_rl_b200.agent import GraphAgent
+    from distributed_rl_b200.apex import default_apex_model
+    from distributed_rl_b200.linear import _stacked_rows
+    from distributed_rl_b200.optim import flat_grads
+    m = GraphAgent(default_apex_model())
+    flat = flat_grads(m.getParameters())
+    assert all(p.grad is not None and p.grad.shape == p.shape and p.grad.stride() == p.stride() for p in m.parameters())
+    assert sum(p.numel() for p in m.parameters()) <= flat.numel() < sum(p.numel() for p in m.parameters()) + 4
+    wa, wv = m.module02.MLP_1.weight, m.module02_1.MLP_1.weight
+    joint = _stacked_rows([wa.grad, wv.grad])
+    assert joint is not None and joint.shape == (1024, 3136)
+    joint[:512].fill_(1.0)
+    joint[512:].fill_(2.0)
+    assert float(wa.grad.min()) == 1.0 == float(wa.grad.max()) and float(wv.grad.min()) == 2.0 == float(wv.grad.max())
+    others = [p for p in m.parameters() if p is not wa and p is not wv]
+    assert all(float(p.grad.abs().max()) == 0.0 for p in others)            # nothing else was touched
+    assert _stacked_rows([wv.grad, wa.grad]) is None                         # wrong order
+    assert _stacked_rows([wa.grad, m.module02.MLP_2.weight.grad]) is None    # different widths
+    assert _stacked_rows([torch.zeros(4, 8), torch.zeros(4, 8)]) is None     # separate allocations
